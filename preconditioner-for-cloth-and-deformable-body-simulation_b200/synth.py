@@ -1,0 +1,290 @@
+"""Deterministic synthetic inputs for the MAS preconditioner path.
+
+The reference ships no mesh/Hessian assembly and no collision detection
+(SURVEY §0); the caller owns them.  These generators play the caller for the
+five BASELINE.json configs.  Layouts follow the reference's boundary types:
+
+* positions  float32 [nv,4]  xyzw, w = 0          (SeVec3fSimd, SeVectorSimd.h:45-103)
+* 3x3 blocks float32 [n,9]   column-major m[3j+i]  (SeMatrix3f, SeMatrix.h:681-682)
+* adjacency  int32 starts[nv+1], idx[nnz]          (SeCsr<int>, SeCsr.h:35-173)
+* edges/faces int32 [n,4]                          (Int4, SeSchwarzPreconditioner.h:48-49)
+* EfSet/EeSet/VfSet 48-byte records                (SeCollisionElements.h:33-58)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+EF_DTYPE = np.dtype(
+    {"names": ["eId", "fId", "stiff", "bary", "normal"],
+     "formats": ["<i4", "<i4", "<f4", ("<f4", 3), ("<f4", 4)],
+     "offsets": [0, 4, 8, 12, 32], "itemsize": 48})
+EE_DTYPE = np.dtype(
+    {"names": ["eId0", "eId1", "stiff", "bary", "normal"],
+     "formats": ["<i4", "<i4", "<f4", ("<f4", 2), ("<f4", 4)],
+     "offsets": [0, 4, 8, 16, 32], "itemsize": 48})
+# `pad` is the float at byte 24 that the reference reads as m_bary[2] (cpp:399)
+VF_DTYPE = np.dtype(
+    {"names": ["vId", "fId", "stiff", "bary", "pad", "normal"],
+     "formats": ["<i4", "<i4", "<f4", ("<f4", 2), "<f4", ("<f4", 4)],
+     "offsets": [0, 4, 8, 16, 24, 32], "itemsize": 48})
+STENCIL_DTYPE = np.dtype(
+    {"names": ["n", "nFirst", "index", "weight", "stiff", "direction"],
+     "formats": ["<i4", "<i4", ("<i4", 5), ("<f4", 5), "<f4", ("<f4", 4)],
+     "offsets": [0, 4, 8, 28, 48, 64], "itemsize": 80})
+
+
+@dataclass
+class Mesh:
+    """Everything AllocatePrecoditioner + PreparePreconditioner consume."""
+    name: str
+    nv: int
+    positions: np.ndarray          # [nv,4] f32
+    nbr_starts: np.ndarray         # [nv+1] i32
+    nbr_idx: np.ndarray            # [nnz] i32
+    diag: np.ndarray               # [nv,9] f32 column-major 3x3
+    offdiag: np.ndarray            # [nnz,9] f32 column-major 3x3
+    edges: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.int32))
+    faces: np.ndarray = field(default_factory=lambda: np.zeros((0, 4), np.int32))
+    ef: np.ndarray = field(default_factory=lambda: np.zeros(0, EF_DTYPE))
+    ee: np.ndarray = field(default_factory=lambda: np.zeros(0, EE_DTYPE))
+    vf: np.ndarray = field(default_factory=lambda: np.zeros(0, VF_DTYPE))
+    ef_total: int = 0
+    ee_total: int = 0
+    vf_total: int = 0
+
+    @property
+    def nnz(self) -> int:
+        return int(self.nbr_idx.shape[0])
+
+    @property
+    def ne(self) -> int:
+        return int(self.edges.shape[0])
+
+    @property
+    def nf(self) -> int:
+        return int(self.faces.shape[0])
+
+
+def _csr_from_edge_sequence(nv: int, a: np.ndarray, b: np.ndarray):
+    """adj[a].push(b); adj[b].push(a) for each edge in sequence order."""
+    m = a.shape[0]
+    src = np.empty(2 * m, np.int64)
+    dst = np.empty(2 * m, np.int64)
+    src[0::2], dst[0::2] = a, b
+    src[1::2], dst[1::2] = b, a
+    order = np.argsort(src, kind="stable")          # time order is the array order
+    src, dst = src[order], dst[order]
+    counts = np.bincount(src, minlength=nv)
+    starts = np.zeros(nv + 1, np.int64)
+    np.cumsum(counts, out=starts[1:])
+    return starts.astype(np.int32), dst.astype(np.int32), src.astype(np.int32)
+
+
+def _spring_hessian(positions, starts, idx, src, k, m, skew=0.0):
+    """K = k d d^T + 0.1 k I per directed edge; offdiag = -K; diag = m I + sum K.
+
+    `skew` adds an antisymmetric part S to the off-diagonal blocks
+    (A(v,u) = -(K+S), A(u,v) = -(K+S)^T) to exercise the column-major
+    convention with non-symmetric 3x3 blocks (FEM-like fill)."""
+    nv = positions.shape[0]
+    p = positions[:, :3].astype(np.float32)
+    d = p[idx] - p[src]
+    ln = np.sqrt((d * d).sum(1, dtype=np.float32)).astype(np.float32)
+    d = (d / ln[:, None]).astype(np.float32)
+    K = (np.float32(k) * d[:, :, None] * d[:, None, :]).astype(np.float32)
+    K += (np.float32(0.1 * k) * np.eye(3, dtype=np.float32))[None]
+    off = -K                                         # [nnz, i, j]
+    if skew != 0.0:
+        lo = np.minimum(src, idx).astype(np.int64)
+        hi = np.maximum(src, idx).astype(np.int64)
+        h = ((lo * 2654435761 + hi * 40503) % 1000).astype(np.float32) / np.float32(1000.0)
+        s = (np.float32(skew * k) * (h - np.float32(0.5))).astype(np.float32)
+        sign = np.where(src < idx, np.float32(1), np.float32(-1)).astype(np.float32)
+        S = np.zeros_like(K)
+        S[:, 0, 1] = s * sign; S[:, 1, 0] = -s * sign
+        S[:, 0, 2] = -0.5 * s * sign; S[:, 2, 0] = 0.5 * s * sign
+        S[:, 1, 2] = 0.25 * s * sign; S[:, 2, 1] = -0.25 * s * sign
+        off = off - S
+    diag = np.zeros((nv, 3, 3), np.float32)
+    np.add.at(diag, src, K)
+    diag += (np.float32(m) * np.eye(3, dtype=np.float32))[None]
+    # column-major: m[3j+i] = M(i,j)  => store transpose flattened
+    off_cm = np.ascontiguousarray(off.transpose(0, 2, 1)).reshape(-1, 9)
+    diag_cm = np.ascontiguousarray(diag.transpose(0, 2, 1)).reshape(-1, 9)
+    return diag_cm.astype(np.float32), off_cm.astype(np.float32)
+
+
+def cloth(n: int, k: float = 1000.0, m: float = 1.0, with_topology: bool = False,
+          skew: float = 0.0, spacing: float = 0.01) -> Mesh:
+    """Planar N x N cloth, 8-neighbour springs (BASELINE.md §3 recipe)."""
+    nv = n * n
+    v = np.arange(nv, dtype=np.int64)
+    i, j = v % n, v // n
+    positions = np.zeros((nv, 4), np.float32)
+    positions[:, 0] = (np.float32(spacing) * i.astype(np.float32))
+    positions[:, 1] = (np.float32(spacing) * j.astype(np.float32))
+    right, down = i + 1 < n, j + 1 < n
+    # per v, in order: (v,v+1), (v,v+N), (v,v+N+1), (v+1,v+N)
+    a = np.stack([v, v, v, v + 1], 1)
+    b = np.stack([v + 1, v + n, v + n + 1, v + n], 1)
+    ok = np.stack([right, down, right & down, right & down], 1)
+    a, b = a[ok], b[ok]                               # row-major boolean mask keeps scan order
+    starts, idx, src = _csr_from_edge_sequence(nv, a, b)
+    diag, off = _spring_hessian(positions, starts, idx, src, k, m, skew)
+    mesh = Mesh(f"cloth{n}x{n}", nv, positions, starts, idx, diag, off)
+    if with_topology:
+        mesh.edges, mesh.faces = _cloth_topology(n)
+    return mesh
+
+
+def _cloth_topology(n: int):
+    """Triangles (v,v+1,v+N),(v+1,v+N+1,v+N) and their unique edges as Int4 rows.
+    Only [0],[1] of an edge and [0..2] of a face are read (cpp:338-342)."""
+    v = np.arange(n * n, dtype=np.int64)
+    i, j = v % n, v // n
+    q = v[(i + 1 < n) & (j + 1 < n)]
+    f0 = np.stack([q, q + 1, q + n, np.zeros_like(q)], 1)
+    f1 = np.stack([q + 1, q + n + 1, q + n, np.zeros_like(q)], 1)
+    faces = np.empty((2 * q.shape[0], 4), np.int64)
+    faces[0::2], faces[1::2] = f0, f1
+    e = np.concatenate([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]], 0)
+    e = np.sort(e, 1)
+    e = np.unique(e, axis=0)
+    edges = np.zeros((e.shape[0], 4), np.int64)
+    edges[:, :2] = e
+    edges[:, 2:] = -1
+    return edges.astype(np.int32), faces.astype(np.int32)
+
+
+def add_collisions(mesh: Mesh, n_ef: int, n_ee: int, n_vf: int, seed: int = 7,
+                   local_fraction: float = 0.5, invalid_fraction: float = 0.02) -> Mesh:
+    """Synthetic EF/EE/VF stencils laid out as the reference literally reads them.
+
+    Q2 (cpp:357, 383): eeSets/vfSets are indexed by the GLOBAL stencil index, so
+    all three arrays get ef+ee+vf records and each kind is written at its
+    global slot.  Q3 (cpp:399): VfSet.m_bary[2] reads the padding float at
+    byte 24; we store x+y there so the weight is the intended -(1-x-y).
+    `local_fraction` of the pairs are between nearby primitives so that
+    BuildCollisionConnection (cpp:514-563) actually fires; a few records get
+    negative ids to exercise the skip at cpp:330/359/385."""
+    assert mesh.ne > 0 and mesh.nf > 0, "need edges/faces (with_topology=True)"
+    rng = np.random.RandomState(seed)
+    total = n_ef + n_ee + n_vf
+    ef = np.zeros(total, EF_DTYPE)
+    ee = np.zeros(total, EE_DTYPE)
+    vf = np.zeros(total, VF_DTYPE)
+
+    def unit(k):
+        x = rng.normal(size=(k, 3)).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True).astype(np.float32)
+        out = np.zeros((k, 4), np.float32)
+        out[:, :3] = x
+        return out
+
+    def near(base_count, other_count, k):
+        """index into `other` close (in array order) to a random base index"""
+        base = rng.randint(0, base_count, size=k)
+        far = rng.randint(0, other_count, size=k)
+        scaled = (base.astype(np.float64) * other_count / base_count).astype(np.int64)
+        loc = np.clip(scaled + rng.randint(-3, 4, size=k), 0, other_count - 1)
+        use_local = rng.uniform(size=k) < local_fraction
+        return base, np.where(use_local, loc, far)
+
+    e, f = near(mesh.ne, mesh.nf, n_ef)
+    s = slice(0, n_ef)
+    ef["eId"][s], ef["fId"][s] = e, f
+    ef["stiff"][s] = rng.uniform(10, 1000, n_ef)
+    ef["bary"][s] = np.stack([rng.uniform(0, 1, n_ef), rng.uniform(0, .5, n_ef), rng.uniform(0, .5, n_ef)], 1)
+    ef["normal"][s] = unit(n_ef)
+
+    e0, e1 = near(mesh.ne, mesh.ne, n_ee)
+    s = slice(n_ef, n_ef + n_ee)
+    ee["eId0"][s], ee["eId1"][s] = e0, e1
+    ee["stiff"][s] = rng.uniform(10, 1000, n_ee)
+    ee["bary"][s] = rng.uniform(0, 1, size=(n_ee, 2))
+    ee["normal"][s] = unit(n_ee)
+
+    vv, ff = near(mesh.nv, mesh.nf, n_vf)
+    s = slice(n_ef + n_ee, total)
+    vf["vId"][s], vf["fId"][s] = vv, ff
+    vf["stiff"][s] = rng.uniform(10, 1000, n_vf)
+    bary = rng.uniform(0, .5, size=(n_vf, 2)).astype(np.float32)
+    vf["bary"][s] = bary
+    vf["pad"][s] = bary[:, 0] + bary[:, 1]
+    vf["normal"][s] = unit(n_vf)
+
+    if invalid_fraction > 0:
+        bad = rng.uniform(size=total) < invalid_fraction
+        ef["eId"][bad[:total] & (np.arange(total) < n_ef)] = -1
+        ee["eId1"][bad & (np.arange(total) >= n_ef) & (np.arange(total) < n_ef + n_ee)] = -1
+        vf["fId"][bad & (np.arange(total) >= n_ef + n_ee)] = -1
+
+    mesh.ef, mesh.ee, mesh.vf = ef, ee, vf
+    mesh.ef_total, mesh.ee_total, mesh.vf_total = n_ef, n_ee, n_vf
+    mesh.name += f"+coll{total}"
+    return mesh
+
+
+def tet_cube(nx: int, ny: int, nz: int, k: float = 1000.0, m: float = 1.0,
+             skew: float = 0.05, spacing: float = 0.01) -> Mesh:
+    """Lattice cube with the 6-tet Kuhn split (<=14 neighbours per vertex).
+
+    Kuhn edges of a cell are the 7 offsets with non-negative components
+    (1,0,0),(0,1,0),(0,0,1),(1,1,0),(1,0,1),(0,1,1),(1,1,1); off-diagonal
+    blocks get a small antisymmetric part (arbitrary FEM-like fill)."""
+    nv = nx * ny * nz
+    v = np.arange(nv, dtype=np.int64)
+    i, j, l = v % nx, (v // nx) % ny, v // (nx * ny)
+    positions = np.zeros((nv, 4), np.float32)
+    positions[:, 0] = np.float32(spacing) * i.astype(np.float32)
+    positions[:, 1] = np.float32(spacing) * j.astype(np.float32)
+    positions[:, 2] = np.float32(spacing) * l.astype(np.float32)
+    offs = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)]
+    a_cols, b_cols, ok_cols = [], [], []
+    for (di, dj, dl) in offs:
+        ok = (i + di < nx) & (j + dj < ny) & (l + dl < nz)
+        a_cols.append(v)
+        b_cols.append(v + di + dj * nx + dl * nx * ny)
+        ok_cols.append(ok)
+    a, b, ok = np.stack(a_cols, 1), np.stack(b_cols, 1), np.stack(ok_cols, 1)
+    a, b = a[ok], b[ok]
+    starts, idx, src = _csr_from_edge_sequence(nv, a, b)
+    diag, off = _spring_hessian(positions, starts, idx, src, k, m, skew)
+    return Mesh(f"tet{nx}x{ny}x{nz}", nv, positions, starts, idx, diag, off)
+
+
+def residual(nv: int, seed: int = 1) -> np.ndarray:
+    """r ~ U(-1,1) per component, MT19937(seed), xyz per vertex in order; w = 0."""
+    rng = np.random.RandomState(seed)
+    r = np.zeros((nv, 4), np.float32)
+    r[:, :3] = rng.uniform(-1.0, 1.0, size=(nv, 3)).astype(np.float32)
+    return r
+
+
+def fnv1a_i32(values: np.ndarray) -> int:
+    """h = 2166136261; h = (h ^ x) * 16777619 per int (SURVEY §8c known answers)."""
+    x = np.ascontiguousarray(values).astype(np.uint32, copy=False).ravel()
+    h = np.uint64(2166136261)
+    # vectorising a serial hash is not possible; chunked python loop on uint32
+    h = int(h)
+    for val in x.tolist():
+        h = ((h ^ val) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+def config(index: int) -> Mesh:
+    """BASELINE.json configs[index]."""
+    if index == 0:
+        return cloth(64)
+    if index == 1:
+        mesh = cloth(512, with_topology=True)
+        return add_collisions(mesh, mesh.nv // 16, mesh.nv // 16, mesh.nv // 8)
+    if index == 2:
+        return cloth(1024)
+    if index == 3:
+        return tet_cube(128, 128, 64)
+    if index == 4:
+        return cloth(2048)
+    raise ValueError(index)
