@@ -1,0 +1,163 @@
+/* mas_b200.h — C ABI of the B200-native multilevel additive Schwarz (MAS) preconditioner.
+ *
+ * Drop-in boundary for the one hot path of
+ * V-Sekai/preconditioner-for-cloth-and-deformable-body-simulation:
+ * class SE::SeSchwarzPreconditioner (SeSchwarzPreconditioner.h:37-178).
+ * The reference defines no FFI; these entry points are exactly what a binding
+ * of its three public methods would call.  Plain pointers and sizes only.
+ *
+ *   reference call (SeSchwarzPreconditioner.h)              replacement
+ *   ------------------------------------------------------  ------------------
+ *   m_positions/m_edges/m_faces/m_neighbours (h:44-51)
+ *   + AllocatePrecoditioner(nv, ne, nf)       (h:56)        mas_allocate()
+ *   PreparePreconditioner(diag, offdiag, ranges,
+ *        ef, ee, vf, efCounts, eeCounts, vfCounts) (h:59-60) mas_prepare()
+ *   Preconditioning(z, residual, dim)          (h:63)       mas_apply()
+ *
+ * Array layouts are the reference's own:
+ *   positions / residual / z : 16-byte xyzw float vectors (SeVec3fSimd, SeVectorSimd.h:45-103)
+ *   diag / offdiag           : 36-byte column-major 3x3 floats (SeMatrix3f, SeMatrix.h:681-682)
+ *   edges / faces            : 16-byte Int4 rows (h:48-49); only [0],[1] / [0..2] are read
+ *   nbrStarts / nbrIdx       : SeCsr<int> m_starts / m_idxs (SeCsr.h:35-173), no self entries;
+ *                              offdiag[nbrStarts[i]+k] is A(i, nbrIdx[nbrStarts[i]+k])
+ *   ef / ee / vf             : 48-byte EfSet / EeSet / VfSet records (SeCollisionElements.h:33-58),
+ *                              indexed the way the reference indexes them (global stencil index, cpp:328/357/383)
+ *
+ * Every pointer argument is either HOST memory (as in the reference, whose
+ * caller owns host arrays) or DEVICE memory on the context's GPU, selected per
+ * call by `mem`.  Device pointers avoid the PCIe copies that would otherwise
+ * dwarf the apply.  All work is issued on the context's CUDA stream; host-memory
+ * calls return after the results are in the caller's buffers, device-memory calls
+ * return after enqueueing (mas_prepare synchronises once internally to size
+ * buffers from the actual cluster counts).
+ *
+ * There is no CPU fallback: every entry point fails with MAS_ERR_CUDA if no
+ * sm_100 device is usable.
+ */
+#ifndef MAS_B200_H
+#define MAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mas_context* mas_handle_t;
+
+enum
+{
+	MAS_OK = 0,
+	MAS_ERR_INVALID = 1,   /* bad argument / call order */
+	MAS_ERR_CUDA = 2,      /* CUDA runtime failure (see mas_last_error) */
+	MAS_ERR_UNSUPPORTED = 3 /* e.g. more than 5 levels (Int4 coarse table, cpp:96) */
+};
+
+enum
+{
+	MAS_MEM_HOST = 0,
+	MAS_MEM_DEVICE = 1
+};
+
+/* mas_set_option keys */
+enum
+{
+	/* 0 (default): reproduce SeSchwarzPreconditioner.cpp:1710 — with 5 levels the top level is
+	 * solved but never prolonged.  1: prolong every level. */
+	MAS_OPT_PROLONG_ALL_LEVELS = 0,
+	/* apply kernel variant: 0 = default (best measured), see DESIGN.md */
+	MAS_OPT_APPLY_VARIANT = 1,
+	/* 1 (default): capture the apply launch sequence in a CUDA graph */
+	MAS_OPT_USE_GRAPH = 2
+};
+
+/* mas_get_int keys */
+enum
+{
+	MAS_INT_NUM_VERTS = 0,
+	MAS_INT_NUM_LEVEL = 1,       /* m_numLevel (h:74) */
+	MAS_INT_TOTAL_CLUSTERS = 2,  /* m_totalNumberClusters (h:76) */
+	MAS_INT_NUM_BLOCKS = 3,      /* active 32-node domains over all levels */
+	MAS_INT_STENCIL_NUM = 4,     /* m_stencilNum (h:112) */
+	MAS_INT_NNZ = 5,
+	MAS_INT_APPLY_LAUNCHES = 6,  /* kernels launched per mas_apply */
+	MAS_INT_PACKED_FLOATS_PER_BLOCK = 7,
+	MAS_INT_OWNED_BLOCK_BEGIN = 8,
+	MAS_INT_OWNED_BLOCK_END = 9,
+	MAS_INT_PREPARE_LAUNCHES = 10 /* kernels launched by the last mas_prepare */
+};
+
+/* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */
+enum
+{
+	MAS_ARR_MORTON = 0,              /* uint64[nv]   m_mortonCode (h:105), original order */
+	MAS_ARR_SORTED_GET_ORIGINAL = 1, /* int32[nv]    m_MapperSortedGetOriginal (h:103) */
+	MAS_ARR_ORIGINAL_GET_SORTED = 2, /* int32[nv]    m_mapperOriginalGetSorted (h:104) */
+	MAS_ARR_GOING_NEXT = 3,          /* int32[totalClusters] m_goingNext (h:97) */
+	MAS_ARR_LEVEL_SIZE = 4,          /* int32[(numLevel+1)*2] m_levelSize (h:99) */
+	MAS_ARR_FINE_CONNECT_MASK = 5,   /* uint32[nv]   m_fineConnectMask after PreparePrefixSumL0 (h:90) */
+	MAS_ARR_COARSE_SPACE_TABLE = 6,  /* int32[nv] for level `index`: m_CoarseSpaceTables[index] (h:88) */
+	MAS_ARR_COARSE_TABLES = 7,       /* int32[nv*4]  m_coarseTables (h:96); entries >= numLevel-1 are 0 */
+	MAS_ARR_SORTED_ADJ_STARTS = 8,   /* int32[nv+1]  adjacency in sorted space (m_mappedNeighbors, h:85, as CSR) */
+	MAS_ARR_SORTED_ADJ_IDX = 9,      /* int32[nnz] */
+	MAS_ARR_STENCILS = 10,           /* 80-byte Stencil records [stencilNum] (SeCollisionElements.h:60-69) */
+	MAS_ARR_STENCIL_INDEX_MAPPED = 11, /* int32[stencilNum*5] m_stencilIndexMapped (h:115) */
+	MAS_ARR_DENSE_INVERSE = 12,      /* float[96*96] dense symmetric inverse of 32-node block `index` */
+	MAS_ARR_MAPPED_R = 13,           /* float[totalClusters*4] m_mappedR (h:101) after the last apply (levels >= 1 only; level 0 is not materialised and reads 0) */
+	MAS_ARR_MAPPED_Z = 14,           /* float[totalClusters*4] m_mappedZ (h:102), levels >= 1 only */
+	MAS_ARR_AABB = 15                /* float[8] lower xyzw, upper xyzw (h:79) */
+};
+
+int mas_create(mas_handle_t* out, int device);
+int mas_destroy(mas_handle_t h);
+const char* mas_last_error(mas_handle_t h);
+
+/* cudaStream_t as void*; NULL = the legacy default stream */
+int mas_set_stream(mas_handle_t h, void* cuda_stream);
+int mas_set_option(mas_handle_t h, int key, int value);
+
+/* Shard the 32-node fine domains across `world` GPUs in Morton-contiguous ranges
+ * (SURVEY §8e).  Must precede mas_allocate.  Default: rank 0 of 1. */
+int mas_set_partition(mas_handle_t h, int rank, int world);
+
+/* replaces m_positions/m_edges/m_faces/m_neighbours + AllocatePrecoditioner (h:44-56, cpp:38-65) */
+int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces,
+	const float* positions, const int* edges, const int* faces,
+	const int* nbrStarts, const int* nbrIdx, int mem);
+
+/* replaces PreparePreconditioner (h:59-60, cpp:67-98).  efTotal/eeTotal/vfTotal are the values the
+ * reference reads from efCounts[numEdges], eeCounts[numEdges], vfCounts[numVerts] (cpp:306-308). */
+int mas_prepare(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges,
+	const void* efSets, const void* eeSets, const void* vfSets,
+	unsigned efTotal, unsigned eeTotal, unsigned vfTotal, int mem);
+
+/* replaces Preconditioning (h:63, cpp:100-110); `dim` is unused there and dropped here */
+int mas_apply(mas_handle_t h, float* z, const float* residual, int mem);
+
+/* Multi-GPU (world > 1) phase split.  Between *_begin and *_end the caller sums the exchange
+ * buffer across ranks (one all-reduce over NCCL):
+ *   prepare: coarse-level Galerkin accumulators (FP64);  apply: coarse-level residuals (FP32). */
+int mas_prepare_begin(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges,
+	const void* efSets, const void* eeSets, const void* vfSets,
+	unsigned efTotal, unsigned eeTotal, unsigned vfTotal, int mem);
+int mas_prepare_end(mas_handle_t h);
+int mas_apply_begin(mas_handle_t h, const float* residual, int mem);
+int mas_apply_end(mas_handle_t h, float* z, int mem);
+/* which: 0 = prepare exchange (double), 1 = apply exchange (float). Returns a DEVICE pointer + element count. */
+int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* count);
+
+/* introspection */
+int mas_get_int(mas_handle_t h, int key, long long* out);
+int mas_get_array(mas_handle_t h, int key, int index, void* host_out, size_t bytes);
+
+/* stand-alone helper with the exact bit behaviour of SeMorton64::Encode (SeMorton.h:75-86), evaluated on the GPU */
+int mas_morton_encode(mas_handle_t h, const float* xyz, int count, uint64_t* codes_out);
+
+/* device-side event timing of the last mas_apply / mas_prepare phases, in milliseconds */
+int mas_get_timing(mas_handle_t h, int which, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAS_B200_H */

@@ -1,0 +1,13 @@
+"""B200-native multilevel additive Schwarz (MAS) preconditioner: drop-in for the one hot path of
+V-Sekai/preconditioner-for-cloth-and-deformable-body-simulation (class SE::SeSchwarzPreconditioner).
+
+  csrc/           hand-written sm_100a CUDA kernels + the extern "C" boundary (include/mas_b200.h)
+  schwarz.py      host-side mirror of the reference class over that C ABI (ctypes)
+  synth.py        deterministic synthetic inputs for the BASELINE.json configs
+  pcg.py          caller-side PCG loop (the reference ships none) used for iteration-count parity
+
+The directory name contains hyphens; import it with
+    importlib.import_module("preconditioner-for-cloth-and-deformable-body-simulation_b200")
+"""
+from .schwarz import SeSchwarzPreconditioner, MasError, load_library, LIB_PATH, EXPORTS  # noqa: F401
+from . import synth  # noqa: F401

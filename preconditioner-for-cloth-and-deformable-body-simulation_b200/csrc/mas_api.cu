@@ -1,0 +1,433 @@
+// extern "C" boundary of libmas_b200.so (include/mas_b200.h): argument checking, host<->device staging,
+// CUDA-graph capture of the apply sequence, and read-only introspection for the parity tests.
+#include "mas_internal.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace mas {
+
+bool check(Context* c, cudaError_t e, const char* what)
+{
+	if (e == cudaSuccess) return true;
+	if (c)
+	{
+		c->err = std::string(what) + ": " + cudaGetErrorString(e);
+	}
+	return false;
+}
+
+static int fail(Context* c, int code, const char* msg)
+{
+	if (c) c->err = msg;
+	return code;
+}
+
+static int level_count(int nv)  // ComputeLevelNums (cpp:112-135): number of levels only; sizes come from real counts
+{
+	int n = 1, sz = pad32(nv);
+	while (sz > 32)
+	{
+		sz /= 32;
+		++n;
+		sz = pad32(sz);
+	}
+	return n;
+}
+
+template <typename T>
+static int stage_in(Context* c, DevBuf<T>& buf, const void* src, size_t count, int mem, const T** out)
+{
+	if (mem == MAS_MEM_DEVICE)
+	{
+		*out = reinterpret_cast<const T*>(src);
+		return MAS_OK;
+	}
+	if (int rc = reserve(c, buf, count)) return rc;
+	if (count) MAS_CUDA(c, cudaMemcpyAsync(buf.p, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+	*out = buf.p;
+	return MAS_OK;
+}
+
+static void drop_graph(Context* c)
+{
+	if (c->applyGraph)
+	{
+		cudaGraphExecDestroy(c->applyGraph);
+		c->applyGraph = nullptr;
+	}
+	c->graphR = nullptr;
+	c->graphZ = nullptr;
+}
+
+static void free_all(Context* c)
+{
+	drop_graph(c);
+	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
+	release(c->aabb); release(c->code); release(c->codeSorted); release(c->s2o); release(c->o2s); release(c->iota);
+	release(c->adjStart); release(c->adjIdx); release(c->cubTemp);
+	release(c->stencils); release(c->stencilIdx); release(c->stencilFlag); release(c->stencilSlot);
+	release(c->fineMask);
+	for (int l = 0; l < kMaxLevel; ++l) release(c->cst[l]);
+	release(c->goingNext); release(c->nextMask); release(c->nextId); release(c->bankCount); release(c->bankPrefix);
+	release(c->scanTotal); release(c->coarseTables);
+	release(c->diagIn); release(c->offdiagIn); release(c->rangesIn); release(c->efIn); release(c->eeIn); release(c->vfIn);
+	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
+	release(c->coarseAcc); release(c->packedInv);
+	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
+}
+
+}  // namespace mas
+
+using namespace mas;
+
+extern "C" {
+
+int mas_create(mas_handle_t* out, int device)
+{
+	if (!out) return MAS_ERR_INVALID;
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return MAS_ERR_CUDA;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MAS_ERR_CUDA;
+	if (prop.major != 10) return MAS_ERR_CUDA;  // sm_100a code only; no fallback path exists
+	if (cudaSetDevice(device) != cudaSuccess) return MAS_ERR_CUDA;
+	mas_context* c = new mas_context();
+	c->device = device;
+	c->smCount = prop.multiProcessorCount;
+	cudaEventCreate(&c->evA);
+	cudaEventCreate(&c->evB);
+	*out = c;
+	return MAS_OK;
+}
+
+int mas_destroy(mas_handle_t h)
+{
+	if (!h) return MAS_ERR_INVALID;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	free_all(h);
+	if (h->evA) cudaEventDestroy(h->evA);
+	if (h->evB) cudaEventDestroy(h->evB);
+	delete h;
+	return MAS_OK;
+}
+
+const char* mas_last_error(mas_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+int mas_set_stream(mas_handle_t h, void* cuda_stream)
+{
+	if (!h) return MAS_ERR_INVALID;
+	h->stream = (cudaStream_t)cuda_stream;
+	drop_graph(h);
+	return MAS_OK;
+}
+
+int mas_set_option(mas_handle_t h, int key, int value)
+{
+	if (!h) return MAS_ERR_INVALID;
+	switch (key)
+	{
+	case MAS_OPT_PROLONG_ALL_LEVELS: h->optProlongAll = value ? 1 : 0; break;
+	case MAS_OPT_APPLY_VARIANT: h->optApplyVariant = value; break;
+	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
+	default: return fail(h, MAS_ERR_INVALID, "unknown option");
+	}
+	drop_graph(h);
+	return MAS_OK;
+}
+
+int mas_set_partition(mas_handle_t h, int rank, int world)
+{
+	if (!h || world < 1 || rank < 0 || rank >= world) return MAS_ERR_INVALID;
+	if (h->allocated) return fail(h, MAS_ERR_INVALID, "mas_set_partition must precede mas_allocate");
+	h->rank = rank;
+	h->world = world;
+	return MAS_OK;
+}
+
+int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const float* positions, const int* edges,
+	const int* faces, const int* nbrStarts, const int* nbrIdx, int mem)
+{
+	if (!h || numVerts <= 0 || !positions || !nbrStarts) return MAS_ERR_INVALID;
+	Context* c = h;
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	// Q1 (cpp:44-64): m_frameIndex sticks at 1 after the first call, so the reference sorts exactly once per object
+	if (c->allocated) return MAS_OK;
+	c->nv = numVerts; c->ne = numEdges; c->nf = numFaces;
+	c->nVC = pad32(numVerts);
+	c->numLevel = level_count(numVerts);
+	if (c->numLevel > kMaxLevel) return fail(c, MAS_ERR_UNSUPPORTED, "more than 5 levels (numVerts > 33,554,432)");
+
+	int nnz = 0;
+	if (mem == MAS_MEM_DEVICE)
+	{
+		MAS_CUDA(c, cudaMemcpyAsync(&nnz, nbrStarts + numVerts, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	else
+		nnz = nbrStarts[numVerts];
+	if (nnz < 0 || (nnz > 0 && !nbrIdx)) return fail(c, MAS_ERR_INVALID, "bad adjacency");
+	c->nnz = nnz;
+
+	const float4* dPos; const int* dStarts; const int* dIdx; const int4* dEdges; const int4* dFaces;
+	if (int rc = stage_in(c, c->positions, positions, (size_t)numVerts, mem, &dPos)) return rc;
+	if (int rc = stage_in(c, c->inStarts, nbrStarts, (size_t)numVerts + 1, mem, &dStarts)) return rc;
+	if (int rc = stage_in(c, c->inIdx, nbrIdx, (size_t)nnz, mem, &dIdx)) return rc;
+	// edges/faces are dereferenced again in every PreparePreconditioner (cpp:332-333): keep a device copy
+	if (int rc = reserve(c, c->edges, (size_t)(numEdges > 0 ? numEdges : 1))) return rc;
+	if (int rc = reserve(c, c->faces, (size_t)(numFaces > 0 ? numFaces : 1))) return rc;
+	cudaMemcpyKind kind = mem == MAS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	if (numEdges > 0 && edges) MAS_CUDA(c, cudaMemcpyAsync(c->edges.p, edges, sizeof(int4) * (size_t)numEdges, kind, c->stream));
+	if (numFaces > 0 && faces) MAS_CUDA(c, cudaMemcpyAsync(c->faces.p, faces, sizeof(int4) * (size_t)numFaces, kind, c->stream));
+	(void)dEdges; (void)dFaces;
+
+	// Morton-contiguous shard of fine banks for this rank
+	const int nFine = c->nVC / 32;
+	c->ownFineBegin = (int)((long long)nFine * c->rank / c->world);
+	c->ownFineEnd = (int)((long long)nFine * (c->rank + 1) / c->world);
+
+	if (int rc = order_vertices(c, dPos, dStarts, dIdx)) return rc;
+	c->allocated = true;
+	c->prepared = false;
+	return MAS_OK;
+}
+
+int mas_prepare_begin(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges,
+	const void* efSets, const void* eeSets, const void* vfSets, unsigned efTotal, unsigned eeTotal, unsigned vfTotal, int mem)
+{
+	if (!h || !diagonal || !csrRanges) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (!c->allocated) return fail(c, MAS_ERR_INVALID, "mas_allocate first");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	drop_graph(c);
+	c->prepared = false;
+	c->prepareLaunches = 0;
+	MAS_CUDA(c, cudaEventRecord(c->evA, c->stream));
+
+	const float *dDiag, *dOff; const int* dRanges;
+	if (int rc = stage_in(c, c->diagIn, diagonal, (size_t)c->nv * 9, mem, &dDiag)) return rc;
+	if (int rc = stage_in(c, c->offdiagIn, csrOffDiagonals, (size_t)c->nnz * 9, mem, &dOff)) return rc;
+	if (int rc = stage_in(c, c->rangesIn, csrRanges, (size_t)c->nv + 1, mem, &dRanges)) return rc;
+	const unsigned long long total = (unsigned long long)efTotal + eeTotal + vfTotal;
+	const unsigned char *dEf = nullptr, *dEe = nullptr, *dVf = nullptr;
+	if (total > 0)
+	{
+		if (!efSets || !eeSets || !vfSets) return fail(c, MAS_ERR_INVALID, "stencil totals > 0 but a set pointer is null");
+		// Q2: each kind is read at the GLOBAL stencil index, so the caller's arrays span that far (cpp:328/357/383)
+		size_t efBytes = 48 * (size_t)efTotal, eeBytes = 48 * (size_t)(efTotal + eeTotal), vfBytes = 48 * (size_t)total;
+		if (int rc = stage_in(c, c->efIn, efSets, efBytes, mem, &dEf)) return rc;
+		if (int rc = stage_in(c, c->eeIn, eeSets, eeBytes, mem, &dEe)) return rc;
+		if (int rc = stage_in(c, c->vfIn, vfSets, vfBytes, mem, &dVf)) return rc;
+	}
+	if (int rc = build_stencils(c, dEf, dEe, dVf, efTotal, eeTotal, vfTotal)) return rc;
+	if (int rc = build_hierarchy(c)) return rc;
+
+	// apply-side buffers, sized from the actual hierarchy; padding slots stay zero for the lifetime of this setup
+	const size_t nc = (size_t)(c->nCoarseNodes > 0 ? c->nCoarseNodes : 1);
+	if (int rc = reserve(c, c->coarseR, nc)) return rc;
+	if (int rc = reserve(c, c->coarseZ, nc)) return rc;
+	if (int rc = reserve(c, c->coarseZsum, nc)) return rc;
+	MAS_CUDA(c, cudaMemsetAsync(c->coarseR.p, 0, sizeof(float4) * nc, c->stream));
+	MAS_CUDA(c, cudaMemsetAsync(c->coarseZ.p, 0, sizeof(float4) * nc, c->stream));
+	MAS_CUDA(c, cudaMemsetAsync(c->coarseZsum.p, 0, sizeof(float4) * nc, c->stream));
+
+	return assemble_and_invert_begin(c, dDiag, dOff, dRanges);
+}
+
+int mas_prepare_end(mas_handle_t h)
+{
+	if (!h) return MAS_ERR_INVALID;
+	Context* c = h;
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = assemble_and_invert_end(c)) return rc;
+	MAS_CUDA(c, cudaEventRecord(c->evB, c->stream));
+	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaEventElapsedTime(&c->lastPrepareMs, c->evA, c->evB);
+	c->prepared = true;
+	return MAS_OK;
+}
+
+int mas_prepare(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const void* efSets,
+	const void* eeSets, const void* vfSets, unsigned efTotal, unsigned eeTotal, unsigned vfTotal, int mem)
+{
+	if (int rc = mas_prepare_begin(h, diagonal, csrOffDiagonals, csrRanges, efSets, eeSets, vfSets, efTotal, eeTotal, vfTotal, mem)) return rc;
+	return mas_prepare_end(h);
+}
+
+static int run_apply_device(Context* c, const float4* r, float4* z)
+{
+	if (c->world > 1 || !c->optUseGraph)
+	{
+		c->applyLaunches = 0;
+		if (int rc = apply_begin(c, r)) return rc;
+		return apply_end(c, r, z);
+	}
+	if (!c->applyGraph || c->graphR != (const float*)r || c->graphZ != (float*)z)
+	{
+		drop_graph(c);
+		cudaStream_t cap;
+		MAS_CUDA(c, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+		cudaStream_t saved = c->stream;
+		c->stream = cap;
+		c->applyLaunches = 0;
+		cudaGraph_t graph = nullptr;
+		int rc = MAS_OK;
+		if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
+		if (rc == MAS_OK) rc = apply_begin(c, r);
+		if (rc == MAS_OK) rc = apply_end(c, r, z);
+		cudaError_t e = cudaStreamEndCapture(cap, &graph);
+		c->stream = saved;
+		if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;
+		if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&c->applyGraph, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
+		if (graph) cudaGraphDestroy(graph);
+		cudaStreamDestroy(cap);
+		if (rc != MAS_OK) { c->applyGraph = nullptr; return rc; }
+		c->graphR = (const float*)r;
+		c->graphZ = (float*)z;
+	}
+	MAS_CUDA(c, cudaGraphLaunch(c->applyGraph, c->stream));
+	return MAS_OK;
+}
+
+int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
+{
+	if (!h || !z || !residual) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (!c->prepared) return fail(c, MAS_ERR_INVALID, "mas_prepare first");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
+	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
+	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
+	MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, sizeof(float4) * (size_t)c->nv, cudaMemcpyHostToDevice, c->stream));
+	if (int rc = run_apply_device(c, c->rIn.p, c->zOut.p)) return rc;
+	// a shard only produces its own vertices' z; copy everything, the caller merges shards
+	MAS_CUDA(c, cudaMemcpyAsync(z, c->zOut.p, sizeof(float4) * (size_t)c->nv, cudaMemcpyDeviceToHost, c->stream));
+	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	return MAS_OK;
+}
+
+int mas_apply_begin(mas_handle_t h, const float* residual, int mem)
+{
+	if (!h || !residual) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (!c->prepared) return fail(c, MAS_ERR_INVALID, "mas_prepare first");
+	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	c->applyLaunches = 0;
+	c->graphR = residual;
+	return apply_begin(c, (const float4*)residual);
+}
+
+int mas_apply_end(mas_handle_t h, float* z, int mem)
+{
+	if (!h || !z) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	return apply_end(c, (const float4*)c->graphR, (float4*)z);
+}
+
+int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* count)
+{
+	if (!h || !device_ptr || !count) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (which == 0) { *device_ptr = c->coarseAcc.p; *count = c->coarseAccCount; return MAS_OK; }
+	if (which == 1) { *device_ptr = c->coarseR.p; *count = (size_t)c->nCoarseNodes * 4; return MAS_OK; }
+	return MAS_ERR_INVALID;
+}
+
+int mas_get_int(mas_handle_t h, int key, long long* out)
+{
+	if (!h || !out) return MAS_ERR_INVALID;
+	Context* c = h;
+	switch (key)
+	{
+	case MAS_INT_NUM_VERTS: *out = c->nv; break;
+	case MAS_INT_NUM_LEVEL: *out = c->numLevel; break;
+	case MAS_INT_TOTAL_CLUSTERS: *out = c->totalClusters; break;
+	case MAS_INT_NUM_BLOCKS: *out = c->nBlocks; break;
+	case MAS_INT_STENCIL_NUM: *out = c->nStencil; break;
+	case MAS_INT_NNZ: *out = c->nnz; break;
+	case MAS_INT_APPLY_LAUNCHES: *out = c->applyLaunches; break;
+	case MAS_INT_PACKED_FLOATS_PER_BLOCK: *out = kTri; break;
+	case MAS_INT_OWNED_BLOCK_BEGIN: *out = c->ownFineBegin; break;
+	case MAS_INT_OWNED_BLOCK_END: *out = c->ownFineEnd; break;
+	case MAS_INT_PREPARE_LAUNCHES: *out = c->prepareLaunches; break;
+	default: return fail(c, MAS_ERR_INVALID, "unknown int key");
+	}
+	return MAS_OK;
+}
+
+static int copy_out(Context* c, const void* dev, size_t have, void* host, size_t bytes)
+{
+	if (bytes > have) return fail(c, MAS_ERR_INVALID, "host buffer larger than the array");
+	MAS_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	return MAS_OK;
+}
+
+int mas_get_array(mas_handle_t h, int key, int index, void* host_out, size_t bytes)
+{
+	if (!h || !host_out) return MAS_ERR_INVALID;
+	Context* c = h;
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	const size_t nv = (size_t)c->nv;
+	switch (key)
+	{
+	case MAS_ARR_MORTON: return copy_out(c, c->code.p, 8 * nv, host_out, bytes);
+	case MAS_ARR_SORTED_GET_ORIGINAL: return copy_out(c, c->s2o.p, 4 * nv, host_out, bytes);
+	case MAS_ARR_ORIGINAL_GET_SORTED: return copy_out(c, c->o2s.p, 4 * nv, host_out, bytes);
+	case MAS_ARR_GOING_NEXT: return copy_out(c, c->goingNext.p, 4 * (size_t)c->totalClusters, host_out, bytes);
+	case MAS_ARR_LEVEL_SIZE:
+	{
+		size_t have = sizeof(int) * 2 * (size_t)(c->numLevel + 1);
+		if (bytes > have) return fail(c, MAS_ERR_INVALID, "host buffer larger than the array");
+		std::memcpy(host_out, c->levelSize, bytes);
+		return MAS_OK;
+	}
+	case MAS_ARR_FINE_CONNECT_MASK: return copy_out(c, c->fineMask.p, 4 * nv, host_out, bytes);
+	case MAS_ARR_COARSE_SPACE_TABLE:
+		if (index < 0 || index >= c->numLevel) return fail(c, MAS_ERR_INVALID, "level out of range");
+		return copy_out(c, c->cst[index].p, 4 * nv, host_out, bytes);
+	case MAS_ARR_COARSE_TABLES: return copy_out(c, c->coarseTables.p, 16 * nv, host_out, bytes);
+	case MAS_ARR_SORTED_ADJ_STARTS: return copy_out(c, c->adjStart.p, 4 * (nv + 1), host_out, bytes);
+	case MAS_ARR_SORTED_ADJ_IDX: return copy_out(c, c->adjIdx.p, 4 * (size_t)c->nnz, host_out, bytes);
+	case MAS_ARR_STENCILS: return copy_out(c, c->stencils.p, 80 * (size_t)c->nStencil, host_out, bytes);
+	case MAS_ARR_STENCIL_INDEX_MAPPED: return copy_out(c, c->stencilIdx.p, 20 * (size_t)c->nStencil, host_out, bytes);
+	case MAS_ARR_DENSE_INVERSE:
+		if (index < 0 || index >= c->nBlocks || bytes != sizeof(float) * kDof * kDof) return fail(c, MAS_ERR_INVALID, "bad block / size");
+		return unpack_dense_inverse(c, index, (float*)host_out);
+	case MAS_ARR_MAPPED_R:
+	case MAS_ARR_MAPPED_Z:
+	{
+		// levels >= 1 only; level-0 entries are not materialised on the device and read as 0
+		size_t have = 16 * (size_t)c->totalClusters;
+		if (bytes > have) return fail(c, MAS_ERR_INVALID, "host buffer larger than the array");
+		std::memset(host_out, 0, bytes);
+		size_t skip = 16 * (size_t)c->nVC;
+		if (bytes <= skip) return MAS_OK;
+		const float4* src = key == MAS_ARR_MAPPED_R ? c->coarseR.p : c->coarseZ.p;
+		return copy_out(c, src, 16 * (size_t)c->nCoarseNodes, (char*)host_out + skip, bytes - skip);
+	}
+	case MAS_ARR_AABB: return copy_out(c, c->aabb.p, 32, host_out, bytes);
+	default: return fail(c, MAS_ERR_INVALID, "unknown array key");
+	}
+}
+
+int mas_morton_encode(mas_handle_t h, const float* xyz, int count, uint64_t* codes_out)
+{
+	if (!h || !xyz || !codes_out || count <= 0) return MAS_ERR_INVALID;
+	MAS_CUDA(h, cudaSetDevice(h->device));
+	return morton_encode_points(h, xyz, count, (unsigned long long*)codes_out);
+}
+
+int mas_get_timing(mas_handle_t h, int which, float* ms_out)
+{
+	if (!h || !ms_out) return MAS_ERR_INVALID;
+	*ms_out = which == 0 ? h->lastPrepareMs : h->lastApplyMs;
+	return MAS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// Per-PCG-iteration apply: z = sum_levels P_l * blockdiag(A_l)^-1 * P_l^T r.
+// Replaces Preconditioning (SeSchwarzPreconditioner.cpp:100-110): the two memsets (102-103),
+// BuildResidualHierarchy (1548-1598), SchwarzLocalXSym (1600-1696) and CollectFinalZ (1698-1719).
+//
+// Launch sequence (captured once in a CUDA graph):
+//   1 restrict_fine     r (original order) -> level-1 residuals; level 0 is never materialised
+//   2 restrict_coarse   level l -> l+1, one launch per level (tiny)
+//   3 solve_coarse      Z_l = inv_l * R_l for every block of levels >= 1
+//   4 prolong_sum       per level-1 node: Z_1 + Z_2[parent] + ... (what CollectFinalZ adds to each of its vertices)
+//   5 solve_fine        gathers r again (L2 resident), multiplies by the packed level-0 inverse, adds the level-1
+//                       sum of step 4 and scatters z straight to original order
+// Step 5 moves 97 % of the bytes: 18,624 B of packed inverse per 32 vertices against 32 x (16+16) B of r/z,
+// i.e. ~1 FLOP per byte, HBM-bound.  One warp owns one domain; lane i owns node i (3 rows).  The packed layout
+// (mas_internal.h) makes every load a fully coalesced 512-byte LDG.128 per warp; the symmetric half of each
+// 3x3 block is applied through two warp shuffles (x of the column node in, B^T x back out), so each matrix
+// element is read exactly once from HBM and never staged.
+//
+// Every sum is evaluated in a fixed order (no float atomics): results are run-to-run deterministic.
+#include "mas_internal.h"
+
+namespace mas {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kApplyThreads = 256;
+constexpr int kWarpsPerCta = kApplyThreads / 32;
+
+// streaming 128-bit load: read-only path, no L1 allocation (each byte is used once)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p)
+{
+	float4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p)
+{
+	float v;
+	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+	return v;
+}
+
+struct Vec3
+{
+	float x, y, z;
+};
+
+// one full cyclic block diagonal d: lane i holds B = A(i, (i+d)&31) row-major in b[0..8]
+__device__ __forceinline__ void apply_block(const float* b, int d, int lane, const Vec3& x, Vec3& y)
+{
+	const int src = (lane + d) & 31, dst = (lane - d) & 31;
+	const float xjx = __shfl_sync(kFull, x.x, src), xjy = __shfl_sync(kFull, x.y, src), xjz = __shfl_sync(kFull, x.z, src);
+	y.x = fmaf(b[0], xjx, fmaf(b[1], xjy, fmaf(b[2], xjz, y.x)));
+	y.y = fmaf(b[3], xjx, fmaf(b[4], xjy, fmaf(b[5], xjz, y.y)));
+	y.z = fmaf(b[6], xjx, fmaf(b[7], xjy, fmaf(b[8], xjz, y.z)));
+	const float tx = fmaf(b[0], x.x, fmaf(b[3], x.y, b[6] * x.z));
+	const float ty = fmaf(b[1], x.x, fmaf(b[4], x.y, b[7] * x.z));
+	const float tz = fmaf(b[2], x.x, fmaf(b[5], x.y, b[8] * x.z));
+	y.x += __shfl_sync(kFull, tx, dst);
+	y.y += __shfl_sync(kFull, ty, dst);
+	y.z += __shfl_sync(kFull, tz, dst);
+}
+
+// y = (packed symmetric 96x96 block) * x for one domain, one warp, direct coalesced LDG.128 stream
+__device__ __forceinline__ Vec3 solve_domain_ldg(const float* __restrict__ blk, int lane, const Vec3 x)
+{
+	const float4* p4 = reinterpret_cast<const float4*>(blk) + lane;
+	Vec3 y = { 0.f, 0.f, 0.f };
+	float4 bufA[9], bufB[9];
+#pragma unroll
+	for (int q = 0; q < 9; ++q) bufA[q] = ldg_stream4(p4 + 32 * q);
+#pragma unroll
+	for (int q = 0; q < 9; ++q) bufB[q] = ldg_stream4(p4 + 32 * (9 + q));
+	{
+		const float* m = reinterpret_cast<const float*>(bufA);
+#pragma unroll
+		for (int dd = 0; dd < 4; ++dd) apply_block(m + 9 * dd, 1 + dd, lane, x, y);
+	}
+#pragma unroll
+	for (int q = 0; q < 9; ++q) bufA[q] = ldg_stream4(p4 + 32 * (18 + q));
+	{
+		const float* m = reinterpret_cast<const float*>(bufB);
+#pragma unroll
+		for (int dd = 0; dd < 4; ++dd) apply_block(m + 9 * dd, 5 + dd, lane, x, y);
+	}
+	// remainder: slots 27..34 (d = 13,14,15 and 5 of the 6 diagonal floats), the tail float, the half diagonal
+#pragma unroll
+	for (int q = 0; q < 8; ++q) bufB[q] = ldg_stream4(p4 + 32 * (27 + q));
+	const float dTail = ldg_stream1(blk + kTailBase + lane);
+	float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+	float h8 = 0.f;
+	if (lane < 16)
+	{
+		const float4* ph = reinterpret_cast<const float4*>(blk + kHalfBase) + lane;
+		h0 = ldg_stream4(ph);
+		h1 = ldg_stream4(ph + 16);
+		h8 = ldg_stream1(blk + kHalfTail + lane);
+	}
+	{
+		const float* m = reinterpret_cast<const float*>(bufA);
+#pragma unroll
+		for (int dd = 0; dd < 4; ++dd) apply_block(m + 9 * dd, 9 + dd, lane, x, y);
+	}
+	{
+		const float* m = reinterpret_cast<const float*>(bufB);
+#pragma unroll
+		for (int dd = 0; dd < 3; ++dd) apply_block(m + 9 * dd, 13 + dd, lane, x, y);
+		// diagonal block, 6 unique floats: (0,0) (1,0) (1,1) (2,0) (2,1) | (2,2) is the tail float
+		const float d0 = m[27], d1 = m[28], d2 = m[29], d3 = m[30], d4 = m[31], d5 = dTail;
+		y.x = fmaf(d0, x.x, fmaf(d1, x.y, fmaf(d3, x.z, y.x)));
+		y.y = fmaf(d1, x.x, fmaf(d2, x.y, fmaf(d4, x.z, y.y)));
+		y.z = fmaf(d3, x.x, fmaf(d4, x.y, fmaf(d5, x.z, y.z)));
+	}
+	{
+		// half diagonal: lanes i < 16 hold B = A(i, i+16)
+		const float b[9] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h8 };
+		const int peer = lane ^ 16;
+		const float xjx = __shfl_sync(kFull, x.x, peer), xjy = __shfl_sync(kFull, x.y, peer), xjz = __shfl_sync(kFull, x.z, peer);
+		float tx = 0.f, ty = 0.f, tz = 0.f;
+		if (lane < 16)
+		{
+			y.x = fmaf(b[0], xjx, fmaf(b[1], xjy, fmaf(b[2], xjz, y.x)));
+			y.y = fmaf(b[3], xjx, fmaf(b[4], xjy, fmaf(b[5], xjz, y.y)));
+			y.z = fmaf(b[6], xjx, fmaf(b[7], xjy, fmaf(b[8], xjz, y.z)));
+			tx = fmaf(b[0], x.x, fmaf(b[3], x.y, b[6] * x.z));
+			ty = fmaf(b[1], x.x, fmaf(b[4], x.y, b[7] * x.z));
+			tz = fmaf(b[2], x.x, fmaf(b[5], x.y, b[8] * x.z));
+		}
+		const float rx = __shfl_sync(kFull, tx, peer), ry = __shfl_sync(kFull, ty, peer), rz = __shfl_sync(kFull, tz, peer);
+		if (lane >= 16) { y.x += rx; y.y += ry; y.z += rz; }
+	}
+	return y;
+}
+
+// Sum `val` over the lanes that share `key` (key < 0: lane takes no part) in a fixed butterfly order and let the
+// lowest lane of each group store it.  All children of a coarse node sit in one bank (clustering is per bank),
+// so a plain store is enough: no atomics, deterministic.
+__device__ __forceinline__ void group_sum_store(int key, Vec3 val, int lane, float4* __restrict__ out, int outBase)
+{
+	unsigned peers = __match_any_sync(kFull, key);
+	unsigned todo = __ballot_sync(kFull, key >= 0 && lane == __ffs(peers) - 1);  // one bit per group (its leader)
+	while (todo)
+	{
+		const int leader = __ffs(todo) - 1;
+		todo &= todo - 1;
+		const unsigned grp = __shfl_sync(kFull, peers, leader);
+		const bool in = (grp >> lane) & 1u;
+		float sx = in ? val.x : 0.f, sy = in ? val.y : 0.f, sz = in ? val.z : 0.f;
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1)
+		{
+			sx += __shfl_xor_sync(kFull, sx, off);
+			sy += __shfl_xor_sync(kFull, sy, off);
+			sz += __shfl_xor_sync(kFull, sz, off);
+		}
+		if (lane == leader) out[key - outBase] = make_float4(sx, sy, sz, 0.f);
+	}
+}
+
+// BuildResidualHierarchy, level 0 -> 1 (cpp:1558-1574)
+__global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const float4* __restrict__ r, const int* __restrict__ s2o,
+	const int* __restrict__ goingNext, int nv, int nVC, int bankBegin, int bankEnd, float4* __restrict__ coarseR)
+{
+	const int lane = threadIdx.x & 31;
+	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (bank >= bankEnd) return;
+	const int v = bank * 32 + lane;
+	int key = -1;
+	Vec3 val = { 0.f, 0.f, 0.f };
+	if (v < nv)
+	{
+		const float4 rv = r[s2o[v]];
+		val.x = rv.x; val.y = rv.y; val.z = rv.z;
+		key = goingNext[v];
+	}
+	group_sum_store(key, val, lane, coarseR, nVC);
+}
+
+// BuildResidualHierarchy, level l -> l+1 for l >= 1 (cpp:1577-1591)
+__global__ void __launch_bounds__(kApplyThreads) restrict_coarse_kernel(const int* __restrict__ goingNext, int begin, int count,
+	int nVC, float4* __restrict__ coarseR)
+{
+	const int lane = threadIdx.x & 31;
+	const int bank = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (bank * 32 >= count) return;
+	const int local = bank * 32 + lane;
+	int key = -1;
+	Vec3 val = { 0.f, 0.f, 0.f };
+	if (local < count)
+	{
+		const float4 rv = coarseR[begin + local - nVC];
+		val.x = rv.x; val.y = rv.y; val.z = rv.z;
+		key = goingNext[begin + local];
+	}
+	group_sum_store(key, val, lane, coarseR, nVC);
+}
+
+// SchwarzLocalXSym on the blocks of levels >= 1 (cpp:1600-1696)
+__global__ void __launch_bounds__(kApplyThreads) solve_coarse_kernel(const float* __restrict__ packed, int nBlocks,
+	const float4* __restrict__ coarseR, float4* __restrict__ coarseZ)
+{
+	const int lane = threadIdx.x & 31;
+	const int blk = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (blk >= nBlocks) return;
+	const float4 rv = coarseR[blk * 32 + lane];
+	const Vec3 x = { rv.x, rv.y, rv.z };
+	const Vec3 y = solve_domain_ldg(packed + (size_t)blk * kTri, lane, x);
+	coarseZ[blk * 32 + lane] = make_float4(y.x, y.y, y.z, 0.f);
+}
+
+// what CollectFinalZ (cpp:1698-1719) adds to every vertex below a level-1 node: Z_1 + Z_2[parent] + ...
+__global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int* __restrict__ goingNext, int begin1, int count1,
+	int nVC, int extraLevels, float4* __restrict__ zsum)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count1) return;
+	int node = begin1 + i;
+	float4 z = coarseZ[node - nVC];
+	for (int l = 0; l < extraLevels; ++l)
+	{
+		node = goingNext[node];
+		const float4 u = coarseZ[node - nVC];
+		z.x += u.x; z.y += u.y; z.z += u.z;
+	}
+	zsum[i] = make_float4(z.x, z.y, z.z, 0.f);
+}
+
+// SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ
+__global__ void __launch_bounds__(kApplyThreads) solve_fine_kernel(const float* __restrict__ packed,
+	const float4* __restrict__ r, const int* __restrict__ s2o, const int* __restrict__ goingNext,
+	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int addCoarse, float4* __restrict__ z)
+{
+	const int lane = threadIdx.x & 31;
+	const int local = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	const int bank = bankBegin + local;
+	if (bank >= bankEnd) return;
+	const int v = bank * 32 + lane;
+	const bool live = v < nv;
+	int ov = 0, parent = 0;
+	Vec3 x = { 0.f, 0.f, 0.f };
+	if (live)
+	{
+		ov = s2o[v];
+		const float4 rv = r[ov];
+		x.x = rv.x; x.y = rv.y; x.z = rv.z;
+		if (addCoarse) parent = goingNext[v];
+	}
+	Vec3 y = solve_domain_ldg(packed + (size_t)local * kTri, lane, x);
+	if (live)
+	{
+		if (addCoarse)
+		{
+			const float4 c = zsum[parent - nVC];
+			y.x += c.x; y.y += c.y; y.z += c.z;
+		}
+		z[ov] = make_float4(y.x, y.y, y.z, 0.f);
+	}
+}
+
+}  // namespace
+
+// number of levels CollectFinalZ prolongs: l = 1 .. min(numLevel,4)-1 (cpp:1710, Q4) unless the fix is requested
+static int prolonged_top(const Context* c)
+{
+	return c->optProlongAll ? c->numLevel : (c->numLevel < 4 ? c->numLevel : 4);
+}
+
+int apply_begin(Context* c, const float4* r)
+{
+	cudaStream_t st = c->stream;
+	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
+	if (c->numLevel < 2) return MAS_OK;
+	if (c->world > 1)
+	{
+		MAS_CUDA(c, cudaMemsetAsync(c->coarseR.p, 0, sizeof(float4) * (size_t)c->nCoarseNodes, st));
+	}
+	if (ownBanks > 0)
+	{
+		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
+			c->ownFineBegin, c->ownFineEnd, c->coarseR.p);
+		c->applyLaunches += 1;
+	}
+	return MAS_OK;
+}
+
+int apply_end(Context* c, const float4* r, float4* z)
+{
+	cudaStream_t st = c->stream;
+	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
+	const int nCoarseBlocks = c->nCoarseNodes / 32;
+	const int top = prolonged_top(c);
+	if (c->numLevel >= 2)
+	{
+		for (int level = 1; level + 1 < c->numLevel; ++level)
+		{
+			const int cnt = c->levelSize[level][0], begin = c->levelSize[level][1];
+			restrict_coarse_kernel<<<cdiv(cdiv(cnt, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin, cnt, c->nVC, c->coarseR.p);
+			c->applyLaunches += 1;
+		}
+		solve_coarse_kernel<<<cdiv(nCoarseBlocks, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p + (size_t)ownBanks * kTri,
+			nCoarseBlocks, c->coarseR.p, c->coarseZ.p);
+		const int cnt1 = c->levelSize[1][0];
+		prolong_sum_kernel<<<cdiv(cnt1, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, c->levelSize[1][1], cnt1, c->nVC, top - 2,
+			c->coarseZsum.p);
+		c->applyLaunches += 2;
+	}
+	if (ownBanks > 0)
+	{
+		solve_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p, r, c->s2o.p, c->goingNext.p,
+			c->coarseZsum.p, c->nv, c->nVC, c->ownFineBegin, c->ownFineEnd, top >= 2 ? 1 : 0, z);
+		c->applyLaunches += 1;
+	}
+	MAS_CUDA(c, cudaGetLastError());
+	return MAS_OK;
+}
+
+}  // namespace mas

@@ -1,0 +1,199 @@
+// Internal definitions shared by the CUDA translation units of libmas_b200.so.
+// Not part of the public boundary (include/mas_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mas_b200.h"
+
+namespace mas {
+
+constexpr int kBank = 32;          // nodes per domain (cpp:139)
+constexpr int kDof = 96;           // 3 * kBank
+constexpr int kTri = 4656;         // 96*97/2 unique floats of a symmetric 96x96 block
+constexpr int kMaxLevel = 5;       // Int4 coarse table (h:96) => at most 5 levels
+constexpr int kMaxCollisionPerVert = 32;  // cpp:187
+
+// ---------------------------------------------------------------------------
+// Packed inverse layout ("lane-slot" layout), 4656 floats = 18,624 bytes per
+// 32-node domain, no padding.  A domain matrix is a 32x32 grid of 3x3 blocks;
+// one warp applies it with lane i owning node i.  Lane i stores
+//   for d = 1..15 : the full 3x3 block A(i, (i+d)%32)            (9 floats each)
+//   then          : the 6 unique floats of its diagonal block A(i,i)
+// = 141 floats, laid out as 35 float4 "slots" [q][lane] (each slot is one fully
+// coalesced 512-byte warp load) plus one trailing float [lane].  The 16 blocks
+// A(i, i+16), i < 16, follow as 2 float4 slots + 1 float over 16 lanes.
+//   floats [   0,4480) : slot q (0..34), lane l  -> 4*(32*q + l) + e,  e = n%4, q = n/4, n < 140
+//   floats [4480,4512) : n = 140 (a22 of the diagonal block), lane l
+//   floats [4512,4640) : half-diagonal, slot q (0..1), lane l<16 -> 4512 + 4*(16*q + l) + e
+//   floats [4640,4656) : half-diagonal float 8, lane l<16
+// Per-lane index n: n = 9*(d-1) + 3*a + b for block d entry (a,b); n = 135 + k6
+// for the diagonal block with k6 = a*(a+1)/2 + b (a >= b).
+// ---------------------------------------------------------------------------
+constexpr int kLaneFloats = 141;
+constexpr int kFullSlots = 35;
+constexpr int kTailBase = 4480;
+constexpr int kHalfBase = 4512;
+constexpr int kHalfTail = 4640;
+
+__host__ __device__ inline int packed_lane_pos(int lane, int n)
+{
+	return n < 140 ? 4 * (32 * (n >> 2) + lane) + (n & 3) : kTailBase + lane;
+}
+__host__ __device__ inline int packed_half_pos(int lane, int n)
+{
+	return n < 8 ? kHalfBase + 4 * (16 * (n >> 2) + lane) + (n & 3) : kHalfTail + lane;
+}
+// position of symmetric entry (r,c) of the 96x96 block, any order of r,c
+__host__ __device__ inline int packed_pos(int r, int c)
+{
+	int i = r / 3, a = r - 3 * i, j = c / 3, b = c - 3 * j;
+	if (i == j)
+	{
+		if (a < b) { int t = a; a = b; b = t; }
+		return packed_lane_pos(i, 135 + a * (a + 1) / 2 + b);
+	}
+	int d = (j - i) & 31;
+	if (d == 16)
+	{
+		if (i > j) { int t = i; i = j; j = t; t = a; a = b; b = t; }
+		return packed_half_pos(i, 3 * a + b);
+	}
+	if (d > 16) { int t = i; i = j; j = t; t = a; a = b; b = t; d = 32 - d; }
+	return packed_lane_pos(i, 9 * (d - 1) + 3 * a + b);
+}
+
+struct Stencil  // SeCollisionElements.h:60-69 byte layout (80 bytes, 16-aligned)
+{
+	int n, nFirst;
+	int index[5];
+	float weight[5];
+	float stiff;
+	float pad_[3];
+	float dir[4];
+};
+static_assert(sizeof(Stencil) == 80, "Stencil must match the reference layout");
+
+template <typename T>
+struct DevBuf
+{
+	T* p = nullptr;
+	size_t cap = 0;  // elements
+};
+
+struct Context
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	int optProlongAll = 0;
+	int optApplyVariant = 0;
+	int optUseGraph = 1;
+	int rank = 0, world = 1;
+	int smCount = 148;
+
+	// ---- allocate-time state
+	bool allocated = false;
+	int nv = 0, ne = 0, nf = 0, nnz = 0, nVC = 0, numLevel = 0;
+	DevBuf<float4> positions;       // staging when the caller passes host memory
+	DevBuf<int4> edges, faces;
+	DevBuf<int> inStarts, inIdx;    // caller adjacency (original space)
+	DevBuf<float> aabb;             // 8 floats
+	DevBuf<unsigned long long> code, codeSorted;
+	DevBuf<int> s2o, o2s, iota;
+	DevBuf<int> adjStart, adjIdx;   // adjacency in sorted space (CSR)
+	DevBuf<unsigned char> cubTemp;
+
+	// ---- prepare-time state
+	bool prepared = false;
+	int nStencil = 0;
+	DevBuf<Stencil> stencils;
+	DevBuf<int> stencilIdx;          // [nStencil][5] sorted-space ids
+	DevBuf<int> stencilFlag, stencilSlot;
+	DevBuf<unsigned> fineMask;       // [nVC]
+	DevBuf<int> cst[kMaxLevel];      // CoarseSpaceTables[level][nv]
+	DevBuf<int> goingNext;
+	DevBuf<unsigned> nextMask;
+	DevBuf<int> nextId;
+	DevBuf<int> bankCount, bankPrefix;
+	DevBuf<int> scanTotal;           // 1 int
+	DevBuf<int4> coarseTables;
+	int levelSize[kMaxLevel + 2][2] = {};
+	int totalClusters = 0;
+	int nBlocks = 0;       // totalClusters / 32
+	int nFineBlocks = 0;   // nVC / 32
+	int nCoarseNodes = 0;  // totalClusters - nVC
+
+	DevBuf<float> diagIn, offdiagIn;     // staging for host inputs
+	DevBuf<int> rangesIn;
+	DevBuf<unsigned char> efIn, eeIn, vfIn;
+	DevBuf<float> extraFine;             // [nv][9] collision self terms (m_additionalHessian32 for vertices)
+	DevBuf<int> cooCount, cooStart, cooFill;  // per fine bank: level-0 collision pair entries
+	DevBuf<float> cooVal;                // [entries][10]: packed (row,col) + 9 floats
+	DevBuf<double> coarseAcc;            // exchange buffer: [nCoarseBlocks][96*96] dense + [nCoarseNodes][9] carry
+	size_t coarseAccCount = 0;
+	DevBuf<float> packedInv;             // [nBlocks][kTri]
+
+	// ---- apply-time state
+	DevBuf<float4> coarseR, coarseZ, coarseZsum;  // indexed by node - nVC
+	DevBuf<float4> rIn, zOut;                      // staging for host r / z
+	cudaGraphExec_t applyGraph = nullptr;
+	const float* graphR = nullptr;
+	float* graphZ = nullptr;
+	int applyLaunches = 0;
+	int prepareLaunches = 0;
+
+	// partition (fine banks owned by this rank)
+	int ownFineBegin = 0, ownFineEnd = 0;
+
+	cudaEvent_t evA = nullptr, evB = nullptr;
+	float lastApplyMs = 0.f, lastPrepareMs = 0.f;
+};
+
+// ---- helpers ---------------------------------------------------------------
+bool check(Context* c, cudaError_t e, const char* what);
+#define MAS_CUDA(c, call)                         \
+	do {                                          \
+		if (!::mas::check((c), (call), #call)) return MAS_ERR_CUDA; \
+	} while (0)
+
+template <typename T>
+int reserve(Context* c, DevBuf<T>& b, size_t n)
+{
+	if (n <= b.cap && b.p) return MAS_OK;
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	size_t want = n ? n : 1;
+	if (!check(c, cudaMalloc((void**)&b.p, want * sizeof(T)), "cudaMalloc")) return MAS_ERR_CUDA;
+	b.cap = want;
+	return MAS_OK;
+}
+template <typename T>
+void release(DevBuf<T>& b)
+{
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr;
+	b.cap = 0;
+}
+
+inline int pad32(int x) { return (x + 31) / 32 * 32; }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- stages (each in its own translation unit) -----------------------------
+int order_vertices(Context* c, const float4* positions, const int* inStarts, const int* inIdx);  // mas_order.cu
+int morton_encode_points(Context* c, const float* xyz, int count, unsigned long long* out);       // mas_order.cu
+int build_stencils(Context* c, const void* ef, const void* ee, const void* vf, unsigned efN, unsigned eeN, unsigned vfN);  // mas_cluster.cu
+int launch_exclusive_scan(Context* c, const int* in, int count, int* out, int* totalOut);                    // mas_cluster.cu
+int build_hierarchy(Context* c);                                                                  // mas_cluster.cu
+int assemble_and_invert_begin(Context* c, const float* diag, const float* offdiag, const int* ranges);  // mas_assemble.cu
+int assemble_and_invert_end(Context* c);                                                          // mas_assemble.cu
+int unpack_dense_inverse(Context* c, int block, float* hostOut);                                  // mas_assemble.cu
+int apply_begin(Context* c, const float4* r);                                                     // mas_apply.cu
+int apply_end(Context* c, const float4* r, float4* z);                                            // mas_apply.cu
+
+}  // namespace mas
+
+struct mas_context : public mas::Context {};
