@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — Preconditioning() applies/s (+ setup ms) of the MAS preconditioner on a 1M-vertex cloth.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config I]
+
+One "step" = one Preconditioning() apply (the per-PCG-iteration hot path, SeSchwarzPreconditioner.cpp:100-110) over
+the whole synthetic mesh.  N>1 is launched by torchrun (one rank per GPU); the 32-node fine domains are sharded in
+Morton-contiguous ranges and the only data-path exchange is one NCCL all-reduce of the coarse-level residuals per
+apply (and one of the coarse Galerkin accumulators per setup).  Total work is fixed as N grows ("strong").
+
+Keys beyond the base contract:
+  value          applies/s with r and z resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e            same metric through the public host-pointer API: pinned host r -> H2D -> apply -> D2H z, every step
+  setup_ms       PreparePreconditioner() per call, device-resident inputs (CUDA events inside the library)
+  roofline       dominant kernel (level-0 solve): algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline   the reference's own CPU code (oracle/_ref, all host threads) on the same mesh; rank 0, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG_NAME = "preconditioner-for-cloth-and-deformable-body-simulation_b200"
+METRIC = "Preconditioning() applies/s, 1M-vert cloth"
+WORKLOADS = {0: "cloth 64x64 (4,096 verts)", 1: "cloth 512x512 (262,144 verts) + EF/EE/VF stencils",
+             2: "cloth 1024x1024 (1,048,576 verts), 8-neighbour springs, 4 levels",
+             3: "tet cube 128x128x64 (1,048,576 verts)", 4: "cloth 2048x2048 (4,194,304 verts), 5 levels"}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def algorithmic_bytes(n_blocks: int, nv: int) -> int:
+    """packed symmetric FP32 inverses read once + 16 B residual read + 16 B z write per vertex."""
+    return n_blocks * 4656 * 4 + 32 * nv
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def traffic_from_profile():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if present."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("solve_fine_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
+    """Times the reference's own CPU implementation (oracle/_ref = SeSchwarzPreconditioner.cpp compiled here) or, if
+    that shared object did not travel, the plain-C oracle port.  Returns (applies/s, setup_ms, kind)."""
+    from oracle import ref_binding as rb
+    if rb.available():
+        p = rb.RefPreconditioner(threads=threads)
+        kind = "reference"
+    else:
+        from oracle import oracle_binding as ob
+        os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+        p = ob.OraclePreconditioner("f")
+        kind = "port"
+    p.allocate(mesh)
+    p.prepare()                       # first call page-faults the buffers in
+    t0 = time.perf_counter()
+    p.prepare()
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    import numpy as np
+    z = np.zeros_like(r)
+    for _ in range(max(1, warmup)):
+        p.apply(r, out=z)
+    best = float("inf")
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        p.apply(r, out=z)
+        best = min(best, time.perf_counter() - t0)
+    mean = (time.perf_counter() - t_all) / steps
+    return 1.0 / mean, 1.0 / best, setup_ms, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = importlib.import_module(PKG_NAME)
+    mesh = pkg.synth.config(args.config)
+    r = pkg.synth.residual(mesh.nv)
+    threads = host_threads()
+    steps = max(1, min(args.steps, 40))        # bounded: 40 applies of the 1M mesh is ~2 s of CPU work after setup
+    t0 = time.perf_counter()
+    mean_rate, best_rate, setup_ms, kind = cpu_reference_apply(mesh, r, steps, min(args.warmup, 3), threads)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "applies/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / mean_rate, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "nv": mesh.nv, "timing": "host wall clock, mean over steps"},
+        "setup_ms": setup_ms,
+        "cpu_baseline": {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
+                         "sample": f"whole mesh, {steps} applies after 1 setup + warm-up; best single apply {1e3 / best_rate:.2f} ms"},
+        "e2e": {"value": mean_rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    pkg = importlib.import_module(PKG_NAME)
+    S = pkg.synth
+    mesh = S.config(args.config)
+    nv = mesh.nv
+    dev = f"cuda:{local}"
+
+    stream = torch.cuda.current_stream()
+    g = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=stream)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tb = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), np.uint8).copy()).to(dev)
+    g.m_positions = t(mesh.positions)
+    g.m_edges = t(mesh.edges) if mesh.ne else None
+    g.m_faces = t(mesh.faces) if mesh.nf else None
+    g.m_neighbours = (t(mesh.nbr_starts), t(mesh.nbr_idx))
+    g.AllocatePrecoditioner(nv, mesh.ne, mesh.nf)
+    d_in = (t(mesh.diag), t(mesh.offdiag), t(mesh.nbr_starts), tb(mesh.ef) if mesh.ef.size else None,
+            tb(mesh.ee) if mesh.ee.size else None, tb(mesh.vf) if mesh.vf.size else None)
+
+    def prepare():
+        if world == 1:
+            g.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total, mesh.vf_total)
+        else:
+            g.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total,
+                                    mesh.vf_total, phase="begin")
+            dist.all_reduce(g.exchange_tensor(0))
+            g.prepare_end()
+
+    prepare()
+    setup_wall = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        prepare()
+        torch.cuda.synchronize()
+        setup_wall.append((time.perf_counter() - t0) * 1e3)
+    setup_ms = min(setup_wall)
+    setup_device_ms = g.timing_ms(0) if world == 1 else None
+
+    r = t(S.residual(nv))
+    z = torch.zeros_like(r)
+    exch = g.exchange_tensor(1) if world > 1 else None
+
+    def step():
+        if world == 1:
+            g.Preconditioning(z, r)
+        else:
+            g.apply_begin(r)
+            dist.all_reduce(exch)
+            g.apply_end(z)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    # keep the GPU busy long enough for at least a few clock samples: repeat the timed block, keep the best
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tms.item()) / args.steps
+    if rank == 0:
+        # hold the load a little longer so the 50 ms sampler sees the clocks under load
+        t_end = time.perf_counter() + 0.4
+    else:
+        t_end = 0
+    while world == 1 and not args.lean and time.perf_counter() < t_end:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = g.apply_launches
+
+    # ---- e2e: public host-pointer API, pinned host buffers, H2D + apply + D2H inside the timed region
+    r_h = torch.from_numpy(S.residual(nv)).pin_memory()
+    z_h = torch.zeros_like(r_h).pin_memory()
+    r_stage, z_stage = torch.empty_like(r), torch.empty_like(r)
+
+    def e2e_step():
+        if world == 1:
+            g.Preconditioning(z_h, r_h)          # mas_apply(MAS_MEM_HOST): cudaMemcpyAsync in, graph, cudaMemcpyAsync out, sync
+        else:
+            r_stage.copy_(r_h, non_blocking=True)
+            g.apply_begin(r_stage)
+            dist.all_reduce(exch)
+            g.apply_end(z_stage)
+            z_h.copy_(z_stage, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_steps = 1 if args.lean else max(5, min(args.steps, 50))
+    for _ in range(0 if args.lean else 3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_rate = 1.0 / float(e2e_s.item())
+
+    # ---- dominant kernel alone, CUDA events on the launching stream (inside the library), un-captured launches
+    fine_ms = None
+    if world == 1 and not args.lean:
+        g.set_option(3, 1)
+        for _ in range(3):
+            g.Preconditioning(z, r)
+        acc = []
+        for _ in range(max(10, min(args.steps, 100))):
+            g.Preconditioning(z, r)
+            acc.append(g.timing_ms(2))
+        g.set_option(3, 0)
+        acc.sort()
+        fine_ms = sum(acc) / len(acc)
+        fine_ms_med = acc[len(acc) // 2]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_blocks = g.num_blocks
+    lv = g.level_size().tolist()
+    n_fine = ((nv + 31) // 32)
+    peak, peak_src = measured_peak_gbs()
+    roof = None
+    if fine_ms:
+        fine_bytes = algorithmic_bytes(n_fine, nv)
+        achieved = fine_bytes / (fine_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "solve_fine_kernel (level-0 SchwarzLocalXSym fused with gather/prolongation)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": fine_bytes, "kernel_ms_mean": fine_ms, "kernel_ms_median": fine_ms_med,
+                "traffic": traffic_from_profile(),
+                "whole_apply": {"algorithmic_bytes": algorithmic_bytes(n_blocks, nv),
+                                "achieved": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 1e9,
+                                "frac": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 1e9 / peak,
+                                "frac_of_8TBs": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 8e12}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and not args.lean:
+        threads = host_threads()
+        n_cpu = 10
+        mean_rate, best_rate, cpu_setup_ms, kind = cpu_reference_apply(mesh, S.residual(nv), n_cpu, 1, threads)
+        cpu = {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
+               "sample": f"whole {WORKLOADS[args.config]} mesh: 1 setup + 1 warm-up + {n_cpu} timed applies, all host threads",
+               "best_ms": 1e3 / best_rate, "setup_ms": cpu_setup_ms}
+
+    out = {
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "nv": nv, "levels": lv, "blocks": n_blocks,
+                   "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step vs 126 MB L2",
+                   "timing": "CUDA events on the launching stream, max over ranks",
+                   "parallelism": f"morton-sharded x{world}" if world > 1 else "single GPU"},
+        "setup_ms": setup_ms, "setup_device_ms": setup_device_ms,
+        "e2e": {"value": e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv, "d2h_bytes_per_step": 16 * nv,
+                "steps": e2e_steps},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="index into BASELINE.json configs (default 2: 1M-vertex cloth)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

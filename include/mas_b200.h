@@ -69,7 +69,10 @@ enum
 	/* apply kernel variant: 0 = default (best measured), see DESIGN.md */
 	MAS_OPT_APPLY_VARIANT = 1,
 	/* 1 (default): capture the apply launch sequence in a CUDA graph */
-	MAS_OPT_USE_GRAPH = 2
+	MAS_OPT_USE_GRAPH = 2,
+	/* 1: bracket the dominant apply kernel (level-0 solve) with CUDA events on the launching stream so that
+	 * mas_get_timing(h, 2, ..) reports its duration; implies un-captured launches.  Default 0. */
+	MAS_OPT_TIME_KERNELS = 3
 };
 
 /* mas_get_int keys */
@@ -154,7 +157,9 @@ int mas_get_array(mas_handle_t h, int key, int index, void* host_out, size_t byt
 /* stand-alone helper with the exact bit behaviour of SeMorton64::Encode (SeMorton.h:75-86), evaluated on the GPU */
 int mas_morton_encode(mas_handle_t h, const float* xyz, int count, uint64_t* codes_out);
 
-/* device-side event timing of the last mas_apply / mas_prepare phases, in milliseconds */
+/* device-side CUDA-event timing in milliseconds: which = 0 last mas_prepare (whole call), 1 last mas_apply
+ * (whole call, only with MAS_OPT_TIME_KERNELS), 2 level-0 solve kernel of the last mas_apply (only with
+ * MAS_OPT_TIME_KERNELS).  Synchronises the stream. */
 int mas_get_timing(mas_handle_t h, int which, float* ms_out);
 
 #ifdef __cplusplus

@@ -89,9 +89,9 @@ class OraclePreconditioner:
         if rc != 0:
             raise RuntimeError(f"oracle prepare failed: {rc}")
 
-    def apply(self, r: np.ndarray) -> np.ndarray:
+    def apply(self, r: np.ndarray, out=None) -> np.ndarray:
         r = np.ascontiguousarray(r, np.float32)
-        z = np.zeros_like(r)
+        z = np.zeros_like(r) if out is None else out
         self._fn("apply", C.c_int, [C.c_void_p] * 3)(self.h, _p(z), _p(r))
         return z
 

@@ -118,9 +118,9 @@ class RefPreconditioner:
         self.lib.ref_prepare(self.h, _p(m.diag), _p(m.offdiag), _p(m.nbr_starts), _p(ef), _p(ee), _p(vf),
                              m.ef_total, m.ee_total, m.vf_total)
 
-    def apply(self, r: np.ndarray) -> np.ndarray:
+    def apply(self, r: np.ndarray, out=None) -> np.ndarray:
         r = np.ascontiguousarray(r, np.float32)
-        z = np.zeros_like(r)
+        z = np.zeros_like(r) if out is None else out
         self.lib.ref_apply(self.h, _p(z), _p(r))
         return z
 

@@ -98,6 +98,10 @@ int mas_create(mas_handle_t* out, int device)
 	c->smCount = prop.multiProcessorCount;
 	cudaEventCreate(&c->evA);
 	cudaEventCreate(&c->evB);
+	cudaEventCreate(&c->evAp0);
+	cudaEventCreate(&c->evAp1);
+	cudaEventCreate(&c->evF0);
+	cudaEventCreate(&c->evF1);
 	*out = c;
 	return MAS_OK;
 }
@@ -110,6 +114,10 @@ int mas_destroy(mas_handle_t h)
 	free_all(h);
 	if (h->evA) cudaEventDestroy(h->evA);
 	if (h->evB) cudaEventDestroy(h->evB);
+	if (h->evAp0) cudaEventDestroy(h->evAp0);
+	if (h->evAp1) cudaEventDestroy(h->evAp1);
+	if (h->evF0) cudaEventDestroy(h->evF0);
+	if (h->evF1) cudaEventDestroy(h->evF1);
 	delete h;
 	return MAS_OK;
 }
@@ -132,6 +140,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_PROLONG_ALL_LEVELS: h->optProlongAll = value ? 1 : 0; break;
 	case MAS_OPT_APPLY_VARIANT: h->optApplyVariant = value; break;
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
+	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	default: return fail(h, MAS_ERR_INVALID, "unknown option");
 	}
 	drop_graph(h);
@@ -258,11 +267,14 @@ int mas_prepare(mas_handle_t h, const float* diagonal, const float* csrOffDiagon
 
 static int run_apply_device(Context* c, const float4* r, float4* z)
 {
-	if (c->world > 1 || !c->optUseGraph)
+	if (c->world > 1 || !c->optUseGraph || c->optTimeKernels)
 	{
 		c->applyLaunches = 0;
+		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evAp0, c->stream));
 		if (int rc = apply_begin(c, r)) return rc;
-		return apply_end(c, r, z);
+		if (int rc = apply_end(c, r, z)) return rc;
+		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evAp1, c->stream));
+		return MAS_OK;
 	}
 	if (!c->applyGraph || c->graphR != (const float*)r || c->graphZ != (float*)z)
 	{
@@ -426,8 +438,24 @@ int mas_morton_encode(mas_handle_t h, const float* xyz, int count, uint64_t* cod
 int mas_get_timing(mas_handle_t h, int which, float* ms_out)
 {
 	if (!h || !ms_out) return MAS_ERR_INVALID;
-	*ms_out = which == 0 ? h->lastPrepareMs : h->lastApplyMs;
-	return MAS_OK;
+	Context* c = h;
+	*ms_out = 0.f;
+	if (which == 0) { *ms_out = c->lastPrepareMs; return MAS_OK; }
+	if (!c->optTimeKernels) return fail(c, MAS_ERR_INVALID, "set MAS_OPT_TIME_KERNELS first");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	if (which == 1)
+	{
+		MAS_CUDA(c, cudaEventSynchronize(c->evAp1));
+		MAS_CUDA(c, cudaEventElapsedTime(ms_out, c->evAp0, c->evAp1));
+		return MAS_OK;
+	}
+	if (which == 2)
+	{
+		MAS_CUDA(c, cudaEventSynchronize(c->evF1));
+		MAS_CUDA(c, cudaEventElapsedTime(ms_out, c->evF0, c->evF1));
+		return MAS_OK;
+	}
+	return fail(c, MAS_ERR_INVALID, "unknown timing key");
 }
 
 }  // extern "C"

@@ -306,8 +306,10 @@ int apply_end(Context* c, const float4* r, float4* z)
 	}
 	if (ownBanks > 0)
 	{
+		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evF0, st));
 		solve_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p, r, c->s2o.p, c->goingNext.p,
 			c->coarseZsum.p, c->nv, c->nVC, c->ownFineBegin, c->ownFineEnd, top >= 2 ? 1 : 0, z);
+		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evF1, st));
 		c->applyLaunches += 1;
 	}
 	MAS_CUDA(c, cudaGetLastError());

@@ -93,6 +93,7 @@ struct Context
 	int optProlongAll = 0;
 	int optApplyVariant = 0;
 	int optUseGraph = 1;
+	int optTimeKernels = 0;
 	int rank = 0, world = 1;
 	int smCount = 148;
 
@@ -150,7 +151,9 @@ struct Context
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
 
-	cudaEvent_t evA = nullptr, evB = nullptr;
+	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
+	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)
+	cudaEvent_t evF0 = nullptr, evF1 = nullptr;    // level-0 solve kernel (timed mode)
 	float lastApplyMs = 0.f, lastPrepareMs = 0.f;
 };
 
