@@ -1,0 +1,78 @@
+"""Multi-GPU host side: one process per GPU, Morton-contiguous shards of the 32-node fine domains.
+
+The reference is single-process (OpenMP only); this layer is new.  What shards and what is exchanged:
+
+  * fine domains (97 % of the bytes) are split into `world` contiguous ranges of banks in Morton order; rank g
+    assembles, inverts and applies only its own banks and produces z only for its own vertices;
+  * level-1 nodes are owned by exactly one fine bank (clustering is per bank, cpp:565-740), so the restriction
+    r -> R_1 is local; every rank then needs the complete coarse residual, which is ONE sum over ranks of the small
+    coarse buffer per apply (0.54 MB at 1M vertices): `exchange(1)`;
+  * setup has ONE sum over ranks of the coarse Galerkin accumulators (FP64): `exchange(0)`;
+  * levels >= 1 are solved redundantly on every rank (3 % of the blocks), which removes any exchange of z.
+
+`ShardedSchwarzPreconditioner` drives a per-rank engine through begin -> exchange -> end.  The engine is
+`SeSchwarzPreconditioner` (CUDA, exchange buffers are device tensors, NCCL) in production; the CPU tests inject a
+numpy engine and run the same driver over gloo.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+
+def fine_bank_range(n_fine_banks: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of the fine banks rank `rank` owns; identical to mas_allocate's split (csrc/mas_api.cu)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return n_fine_banks * rank // world, n_fine_banks * (rank + 1) // world
+
+
+def owned_vertex_range(nv: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) in SORTED (Morton) vertex ids."""
+    n_banks = (nv + 31) // 32
+    b, e = fine_bank_range(n_banks, rank, world)
+    return min(b * 32, nv), min(e * 32, nv)
+
+
+class ShardedSchwarzPreconditioner:
+    """The reference's three calls (h:55-63) over `world` shards.
+
+    engine must provide: AllocatePrecoditioner, PreparePreconditioner(..., phase="begin"), prepare_end(),
+    apply_begin(r), apply_end(z), exchange_tensor(which) -> torch tensor aliasing the exchange buffer."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.engine = engine
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._apply_exchange = None
+
+    def _sum_over_ranks(self, tensor):
+        if self.world > 1 and tensor.numel():
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def AllocatePrecoditioner(self, numVerts: int, numEdges: int, numFaces: int):  # noqa: N802
+        self.engine.AllocatePrecoditioner(numVerts, numEdges, numFaces)
+
+    def PreparePreconditioner(self, diagonal, csrOffDiagonals, csrRanges, efSets=None, eeSets=None, vfSets=None,  # noqa: N802
+                              efCounts=0, eeCounts=0, vfCounts=0):
+        self.engine.PreparePreconditioner(diagonal, csrOffDiagonals, csrRanges, efSets, eeSets, vfSets, efCounts, eeCounts,
+                                          vfCounts, phase="begin")
+        self._sum_over_ranks(self.engine.exchange_tensor(0))
+        self.engine.prepare_end()
+        self._apply_exchange = self.engine.exchange_tensor(1)   # sized by this setup's hierarchy
+
+    def Preconditioning(self, z, residual, dim: int = 0):  # noqa: N802
+        """z[own vertices] = M^-1 residual; entries of other ranks' vertices are left untouched."""
+        self.engine.apply_begin(residual)
+        self._sum_over_ranks(self._apply_exchange)
+        self.engine.apply_end(z)
+        return z
+
+    def gather_z(self, z, owned_mask):
+        """Debug/test helper: every rank ends with the complete z (sum of the disjoint shards)."""
+        import torch
+        part = torch.where(owned_mask.unsqueeze(-1), z, torch.zeros_like(z))
+        self._sum_over_ranks(part)
+        return part
