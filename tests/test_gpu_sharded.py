@@ -1,0 +1,136 @@
+"""Sharded (multi-GPU) path on real hardware.
+
+  * two shards driven inside ONE process on one GPU (the exchange is done by adding the two exchange tensors): runs on the
+    1-GPU box and exercises exactly the kernels/ranges a 2-GPU job runs;
+  * the real thing over NCCL, one process per GPU, when the box has >= 2 GPUs (skipped otherwise).
+Bar: merged z equals the single-device z to 1e-5 relative L2 (the only difference is the summation order of the FP64
+coarse accumulators), every shard writes only its own vertices, structure identical on every rank."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_NAME = "preconditioner-for-cloth-and-deformable-body-simulation_b200"
+
+
+def _mesh(synth, name):
+    if name == "cloth96_collisions":
+        m = synth.cloth(96, with_topology=True)
+        return synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
+    if name == "cloth50_ragged":
+        return synth.cloth(50)
+    if name == "cloth256":
+        return synth.cloth(256)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth50_ragged", 3), ("cloth256", 4)])
+def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
+    import torch
+    mesh = _mesh(synth, name)
+    r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+    single = pkg.SeSchwarzPreconditioner(0).setup_from_mesh(mesh, device_inputs=True)
+    z1 = torch.empty_like(r)
+    single.Preconditioning(z1, r)
+
+    shards = [pkg.SeSchwarzPreconditioner(0, rank=k, world=world) for k in range(world)]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    raw = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), np.uint8).copy()).cuda()
+    d = dict(pos=dev(mesh.positions), edges=dev(mesh.edges) if mesh.ne else None, faces=dev(mesh.faces) if mesh.nf else None,
+             st=dev(mesh.nbr_starts), ix=dev(mesh.nbr_idx), diag=dev(mesh.diag), off=dev(mesh.offdiag),
+             ef=raw(mesh.ef) if mesh.ef.size else None, ee=raw(mesh.ee) if mesh.ee.size else None, vf=raw(mesh.vf) if mesh.vf.size else None)
+    for g in shards:
+        g.m_positions, g.m_edges, g.m_faces, g.m_neighbours = d["pos"], d["edges"], d["faces"], (d["st"], d["ix"])
+        g.AllocatePrecoditioner(mesh.nv, mesh.ne, mesh.nf)
+        g.PreparePreconditioner(d["diag"], d["off"], d["st"], d["ef"], d["ee"], d["vf"], mesh.ef_total, mesh.ee_total, mesh.vf_total,
+                                phase="begin")
+    torch.cuda.synchronize()
+    total = sum(g.exchange_tensor(0).clone() for g in shards)       # what one all-reduce does
+    for g in shards:
+        g.exchange_tensor(0).copy_(total)
+        g.prepare_end()
+    for g in shards:
+        assert np.array_equal(g.going_next(), single.going_next())
+        assert np.array_equal(g.level_size(), single.level_size())
+
+    zs = [torch.full_like(r, float("nan")) for _ in shards]
+    for g in shards:
+        g.apply_begin(r)
+    torch.cuda.synchronize()
+    total = sum(g.exchange_tensor(1).clone() for g in shards)
+    for g, z in zip(shards, zs):
+        g.exchange_tensor(1).copy_(total)
+        g.apply_end(z)
+    torch.cuda.synchronize()
+    s2o = torch.from_numpy(single.sorted_get_original().astype(np.int64)).cuda()
+    merged = torch.zeros_like(r)
+    covered = torch.zeros(mesh.nv, dtype=torch.int32, device="cuda")
+    for g, z in zip(shards, zs):
+        b, e = g.owned_fine_blocks
+        own = s2o[min(32 * b, mesh.nv):min(32 * e, mesh.nv)]
+        mask = torch.zeros(mesh.nv, dtype=torch.bool, device="cuda")
+        mask[own] = True
+        assert not torch.isnan(z[mask]).any() and torch.isnan(z[~mask]).all()    # a shard writes its own vertices only
+        merged[mask] = z[mask]
+        covered[mask] += 1
+    assert bool((covered == 1).all())
+    assert rel_l2(merged.cpu().numpy(), z1.cpu().numpy()) < 1e-5
+
+
+def _nccl_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        pkg = importlib.import_module(PKG_NAME)
+        part = importlib.import_module(PKG_NAME + ".partition")
+        mesh = pkg.synth.cloth(256)
+        eng = pkg.SeSchwarzPreconditioner(rank, rank=rank, world=world, stream=torch.cuda.current_stream())
+        drv = part.ShardedSchwarzPreconditioner(eng)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        eng.m_positions, eng.m_neighbours = dev(mesh.positions), (dev(mesh.nbr_starts), dev(mesh.nbr_idx))
+        drv.AllocatePrecoditioner(mesh.nv, 0, 0)
+        drv.PreparePreconditioner(dev(mesh.diag), dev(mesh.offdiag), dev(mesh.nbr_starts))
+        r = dev(pkg.synth.residual(mesh.nv))
+        z = torch.zeros_like(r)
+        drv.Preconditioning(z, r)
+        dist.all_reduce(z)                                        # disjoint shards, zeros elsewhere -> the full z
+        torch.cuda.synchronize()
+        if rank == 0:
+            one = pkg.SeSchwarzPreconditioner(0).setup_from_mesh(mesh, device_inputs=True)
+            z1 = torch.empty_like(r)
+            one.Preconditioning(z1, r)
+            torch.cuda.synchronize()
+            q.put(float((z - z1)[:, :3].norm() / z1[:, :3].norm()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpus_over_nccl_match_single_device():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [ctx.Process(target=_nccl_worker, args=(k, 2, port, q)) for k in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) < 1e-5
