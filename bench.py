@@ -147,6 +147,25 @@ def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
     return 1.0 / mean, 1.0 / best, setup_ms, kind
 
 
+def cpu_reference_pcg(mesh, b, threads: int):
+    """PCG to 1e-5 on the host: scipy block-CSR SpMV + the reference's own Preconditioning() (oracle/_ref), all threads."""
+    from oracle import ref_binding as rb
+    from oracle.cpu_pcg import bsr_matrix, cpu_pcg
+    if rb.available():
+        p = rb.RefPreconditioner(threads=threads)
+        kind = "reference"
+    else:
+        from oracle import oracle_binding as ob
+        p = ob.OraclePreconditioner("f")
+        kind = "port"
+    p.allocate(mesh)
+    p.prepare()
+    A = bsr_matrix(mesh)
+    t0 = time.perf_counter()
+    _, its = cpu_pcg(A, b, p.apply)
+    return {"iterations": its, "solve_ms": (time.perf_counter() - t0) * 1e3, "kind": kind, "cores": threads, "tol": 1e-5}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -341,6 +360,23 @@ def run_ours(args):
                                 "frac": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 1e9 / peak,
                                 "frac_of_8TBs": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 8e12}}
 
+    # ---- PCG to 1e-5 with MAS through the device harness (BASELINE config 2: iteration count and wall time)
+    pcg = None
+    if world == 1 and not args.lean:
+        idx_d = t(mesh.nbr_idx)
+        b_d = t(S.residual(nv))
+        pkg.pcg_solve(g, d_in[0], d_in[1], d_in[2], idx_d, b_d)          # warm-up (graph instantiate, workspace)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = pkg.pcg_solve(g, d_in[0], d_in[1], d_in[2], idx_d, b_d)
+        torch.cuda.synchronize()
+        pcg_ms = (time.perf_counter() - t0) * 1e3
+        plain = pkg.pcg_solve(g, d_in[0], d_in[1], d_in[2], idx_d, b_d, use_preconditioner=False, max_iter=5000)
+        pcg = {"tol": 1e-5, "iterations": res.iterations, "converged": res.converged, "rel_residual": res.rel_residual,
+               "solve_ms": pcg_ms, "ms_per_iteration": pcg_ms / max(1, res.iterations),
+               "launches_per_iteration": res.launches_per_iteration, "iterations_unpreconditioned": plain.iterations,
+               "timing": "host wall clock around mas_pcg_solve, device-resident A/b/x"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.lean:
         threads = host_threads()
@@ -349,6 +385,8 @@ def run_ours(args):
         cpu = {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
                "sample": f"whole {WORKLOADS[args.config]} mesh: 1 setup + 1 warm-up + {n_cpu} timed applies, all host threads",
                "best_ms": 1e3 / best_rate, "setup_ms": cpu_setup_ms}
+        if args.cpu_pcg:
+            cpu["pcg"] = cpu_reference_pcg(mesh, S.residual(nv), threads)
 
     out = {
         "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
@@ -362,7 +400,7 @@ def run_ours(args):
         "e2e": {"value": e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv, "d2h_bytes_per_step": 16 * nv,
                 "steps": e2e_steps},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "pcg": pcg,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -378,6 +416,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="index into BASELINE.json configs (default 2: 1M-vertex cloth)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
+    ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -88,7 +88,9 @@ enum
 	MAS_INT_PACKED_FLOATS_PER_BLOCK = 7,
 	MAS_INT_OWNED_BLOCK_BEGIN = 8,
 	MAS_INT_OWNED_BLOCK_END = 9,
-	MAS_INT_PREPARE_LAUNCHES = 10 /* kernels launched by the last mas_prepare */
+	MAS_INT_PREPARE_LAUNCHES = 10, /* kernels launched by the last mas_prepare */
+	MAS_INT_PCG_LAUNCHES_PER_ITER = 11, /* kernels per iteration of the last mas_pcg_solve (its own 4 + the apply's) */
+	MAS_INT_PCG_CONVERGED = 12     /* 1 if the last mas_pcg_solve met its tolerance */
 };
 
 /* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */
@@ -149,6 +151,15 @@ int mas_apply_begin(mas_handle_t h, const float* residual, int mem);
 int mas_apply_end(mas_handle_t h, float* z, int mem);
 /* which: 0 = prepare exchange (double), 1 = apply exchange (float). Returns a DEVICE pointer + element count. */
 int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* count);
+
+/* Caller-side harness (the reference ships no solver): preconditioned conjugate gradients for A x = b with
+ * everything resident on the GPU.  A is given exactly as PreparePreconditioner receives it (original vertex order):
+ * diagonal[nv] and csrOffDiagonals[nnz] 36-byte column-major blocks, csrRanges[nv+1] / csrIdx[nnz] the adjacency CSR
+ * (h:51 m_neighbours).  b, x: 16-byte xyzw vectors, x0 = 0.  Stops when ||r||_2 / ||b||_2 < relTol or after maxIter
+ * iterations; dot products in FP64.  usePreconditioner = 0 runs plain CG (z = r).  Requires mas_prepare when
+ * usePreconditioner != 0.  Single-GPU contexts only. */
+int mas_pcg_solve(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const int* csrIdx,
+	const float* b, float* x, float relTol, int maxIter, int usePreconditioner, int mem, int* itersOut, float* relResOut);
 
 /* introspection */
 int mas_get_int(mas_handle_t h, int key, long long* out);

@@ -75,6 +75,8 @@ static void free_all(Context* c)
 	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
 	release(c->coarseAcc); release(c->packedInv);
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
+	release(c->pcgR); release(c->pcgZ); release(c->pcgP); release(c->pcgAp); release(c->pcgB); release(c->pcgX);
+	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);
 }
 
 }  // namespace mas
@@ -341,6 +343,37 @@ int mas_apply_end(mas_handle_t h, float* z, int mem)
 	return apply_end(c, (const float4*)c->graphR, (float4*)z);
 }
 
+int mas_pcg_solve(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const int* csrIdx,
+	const float* b, float* x, float relTol, int maxIter, int usePreconditioner, int mem, int* itersOut, float* relResOut)
+{
+	if (!h || !diagonal || !csrRanges || !b || !x || maxIter < 0 || !(relTol > 0.f)) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (!c->allocated) return fail(c, MAS_ERR_INVALID, "mas_allocate first");
+	if (usePreconditioner && !c->prepared) return fail(c, MAS_ERR_INVALID, "mas_prepare first");
+	if (c->world > 1) return fail(c, MAS_ERR_UNSUPPORTED, "mas_pcg_solve runs on single-GPU contexts");
+	if (c->nnz > 0 && (!csrOffDiagonals || !csrIdx)) return fail(c, MAS_ERR_INVALID, "off-diagonal arrays missing");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	const float *dDiag, *dOff; const int *dRanges, *dIdx; const float4* dB;
+	if (int rc = stage_in(c, c->pcgDiag, diagonal, (size_t)c->nv * 9, mem, &dDiag)) return rc;
+	if (int rc = stage_in(c, c->pcgOff, csrOffDiagonals, (size_t)c->nnz * 9, mem, &dOff)) return rc;
+	if (int rc = stage_in(c, c->pcgRanges, csrRanges, (size_t)c->nv + 1, mem, &dRanges)) return rc;
+	if (int rc = stage_in(c, c->pcgIdx, csrIdx, (size_t)c->nnz, mem, &dIdx)) return rc;
+	if (int rc = stage_in(c, c->pcgB, b, (size_t)c->nv, mem, &dB)) return rc;
+	float4* dX = (float4*)x;
+	if (mem != MAS_MEM_DEVICE)
+	{
+		if (int rc = reserve(c, c->pcgX, (size_t)c->nv)) return rc;
+		dX = c->pcgX.p;
+	}
+	if (int rc = pcg_solve(c, dDiag, dOff, dRanges, dIdx, dB, dX, relTol, maxIter, usePreconditioner ? 1 : 0, itersOut, relResOut)) return rc;
+	if (mem != MAS_MEM_DEVICE)
+	{
+		MAS_CUDA(c, cudaMemcpyAsync(x, dX, sizeof(float4) * (size_t)c->nv, cudaMemcpyDeviceToHost, c->stream));
+		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	return MAS_OK;
+}
+
 int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* count)
 {
 	if (!h || !device_ptr || !count) return MAS_ERR_INVALID;
@@ -367,6 +400,8 @@ int mas_get_int(mas_handle_t h, int key, long long* out)
 	case MAS_INT_OWNED_BLOCK_BEGIN: *out = c->ownFineBegin; break;
 	case MAS_INT_OWNED_BLOCK_END: *out = c->ownFineEnd; break;
 	case MAS_INT_PREPARE_LAUNCHES: *out = c->prepareLaunches; break;
+	case MAS_INT_PCG_LAUNCHES_PER_ITER: *out = c->pcgLaunchesPerIter; break;
+	case MAS_INT_PCG_CONVERGED: *out = c->pcgConverged; break;
 	default: return fail(c, MAS_ERR_INVALID, "unknown int key");
 	}
 	return MAS_OK;

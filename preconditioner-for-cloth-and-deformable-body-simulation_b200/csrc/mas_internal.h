@@ -148,6 +148,15 @@ struct Context
 	int applyLaunches = 0;
 	int prepareLaunches = 0;
 
+	// ---- PCG harness workspace (mas_pcg.cu)
+	DevBuf<float4> pcgR, pcgZ, pcgP, pcgAp, pcgB, pcgX;
+	DevBuf<double> pcgPartials;
+	DevBuf<unsigned char> pcgState;
+	DevBuf<float> pcgDiag, pcgOff;
+	DevBuf<int> pcgRanges, pcgIdx;
+	int pcgLaunchesPerIter = 0;
+	int pcgConverged = 0;
+
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
 
@@ -196,6 +205,8 @@ int assemble_and_invert_end(Context* c);                                        
 int unpack_dense_inverse(Context* c, int block, float* hostOut);                                  // mas_assemble.cu
 int apply_begin(Context* c, const float4* r);                                                     // mas_apply.cu
 int apply_end(Context* c, const float4* r, float4* z);                                            // mas_apply.cu
+int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges, const int* idx, const float4* b, float4* x,
+	float relTol, int maxIter, int usePrecond, int* itersOut, float* relResOut);                  // mas_pcg.cu
 
 }  // namespace mas
 

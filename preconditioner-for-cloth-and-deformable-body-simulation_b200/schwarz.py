@@ -22,7 +22,8 @@ LIB_PATH = os.path.join(_HERE, "libmas_b200.so")
 MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
 OPT_PROLONG_ALL_LEVELS, OPT_APPLY_VARIANT, OPT_USE_GRAPH, OPT_TIME_KERNELS = 0, 1, 2, 3
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
- INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES) = range(11)
+ INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
+ INT_PCG_CONVERGED) = range(13)
 (ARR_MORTON, ARR_SORTED_GET_ORIGINAL, ARR_ORIGINAL_GET_SORTED, ARR_GOING_NEXT, ARR_LEVEL_SIZE, ARR_FINE_CONNECT_MASK,
  ARR_COARSE_SPACE_TABLE, ARR_COARSE_TABLES, ARR_SORTED_ADJ_STARTS, ARR_SORTED_ADJ_IDX, ARR_STENCILS,
  ARR_STENCIL_INDEX_MAPPED, ARR_DENSE_INVERSE, ARR_MAPPED_R, ARR_MAPPED_Z, ARR_AABB) = range(16)
@@ -32,6 +33,7 @@ EXPORTS = [
     "mas_create", "mas_destroy", "mas_last_error", "mas_set_stream", "mas_set_option", "mas_set_partition",
     "mas_allocate", "mas_prepare", "mas_apply", "mas_prepare_begin", "mas_prepare_end", "mas_apply_begin",
     "mas_apply_end", "mas_exchange_buffer", "mas_get_int", "mas_get_array", "mas_morton_encode", "mas_get_timing",
+    "mas_pcg_solve",
 ]
 
 _lib = None
@@ -70,6 +72,7 @@ def load_library() -> C.CDLL:
     lib.mas_get_array.argtypes = [vp, i, i, vp, C.c_size_t]
     lib.mas_morton_encode.argtypes = [vp, vp, i, vp]
     lib.mas_get_timing.argtypes = [vp, i, C.POINTER(C.c_float)]
+    lib.mas_pcg_solve.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_float, i, i, i, C.POINTER(i), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "mas_last_error":
             getattr(lib, name).restype = i

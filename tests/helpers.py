@@ -67,3 +67,6 @@ def arbiter_ok(z_test, z_ref32, z_f64, slack=2.0, floor=1e-6):
     e_test = rel_l2(z_test, z_f64) * nz
     e_ref = rel_l2(z_ref32, z_f64) * nz
     return e_test <= slack * e_ref + floor * nz, e_test / nz, e_ref / nz
+
+
+from oracle.cpu_pcg import bsr_matrix, cpu_pcg  # noqa: E402,F401  (test-infrastructure PCG loop)

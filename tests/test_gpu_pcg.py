@@ -1,0 +1,71 @@
+"""PCG iteration-count parity (north_star: "the same PCG iteration counts to convergence"): the device PCG harness
+(mas_pcg_solve: block-CSR SpMV + fused dot/axpy + the MAS apply, one CUDA graph per iteration) against the same loop on the
+CPU preconditioned by the REFERENCE's own Preconditioning() (oracle/_ref, one thread) — or, where that shared object is
+absent, by the FP64 arbiter build of the oracle, which gives the reference's counts on every mesh tried (the FP32
+restatement does not on the small tet cube: 67 vs the reference's 83-84).
+Bar: iteration count within +-2 % (at least +-1), and the solution itself."""
+import numpy as np
+import pytest
+
+from helpers import bsr_matrix, cpu_pcg, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["cloth96", "cloth128_collisions", "tet16x16x8", "cloth50_ragged"])
+def test_iteration_count_matches_cpu_pcg_with_oracle(name, pkg, synth, oracle_lib):
+    if name == "cloth96":
+        mesh = synth.cloth(96)
+    elif name == "cloth128_collisions":
+        m = synth.cloth(128, with_topology=True)
+        mesh = synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
+    elif name == "tet16x16x8":
+        mesh = synth.tet_cube(16, 16, 8)
+    else:
+        mesh = synth.cloth(50)
+    A = bsr_matrix(mesh)
+    b = synth.residual(mesh.nv)
+    from oracle import ref_binding as rb
+    if rb.available():
+        o = rb.RefPreconditioner(threads=1)
+        o.allocate(mesh)
+        o.prepare()
+    else:
+        o = make_oracle(oracle_lib, mesh, "d")
+    x_ref, it_ref = cpu_pcg(A, b, o.apply)
+    _, it_plain = cpu_pcg(A, b, None)
+
+    g = pkg.SeSchwarzPreconditioner(0).setup_from_mesh(mesh)
+    res = pkg.pcg_solve(g, mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.nbr_idx, b)
+    assert res.converged and res.rel_residual < 1e-5
+    slack = max(1, int(round(0.02 * it_ref)))
+    assert abs(res.iterations - it_ref) <= slack, (res.iterations, it_ref)
+    # the true residual of the returned x, evaluated in FP64 on the CPU
+    A64 = bsr_matrix(mesh, np.float64)
+    x = np.asarray(res.x)[:, :3].astype(np.float64).reshape(-1)
+    bb = b[:, :3].astype(np.float64).reshape(-1)
+    assert np.linalg.norm(bb - A64 @ x) / np.linalg.norm(bb) < 5e-5
+    assert np.linalg.norm(x.reshape(-1, 3) - x_ref) / np.linalg.norm(x_ref) < 1e-3
+    # plain CG through the same harness: same count as the CPU loop, and MAS really pays
+    plain = pkg.pcg_solve(g, mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.nbr_idx, b, use_preconditioner=False)
+    assert abs(plain.iterations - it_plain) <= max(2, int(round(0.02 * it_plain))), (plain.iterations, it_plain)
+    assert res.iterations * 2 < plain.iterations
+    assert res.launches_per_iteration == 4 + g.apply_launches or g.apply_launches == 0
+
+
+def test_pcg_device_pointers_and_determinism(pkg, synth):
+    import torch
+    mesh = synth.cloth(128)
+    g = pkg.SeSchwarzPreconditioner(0).setup_from_mesh(mesh, device_inputs=True)
+    d = g._dev_inputs
+    idx = torch.from_numpy(mesh.nbr_idx).cuda()
+    b = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+    r1 = pkg.pcg_solve(g, d[0], d[1], d[2], idx, b)
+    r2 = pkg.pcg_solve(g, d[0], d[1], d[2], idx, b)
+    torch.cuda.synchronize()
+    assert r1.iterations == r2.iterations and torch.equal(r1.x, r2.x)          # fixed reduction order
+    host = pkg.pcg_solve(g, mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.nbr_idx, synth.residual(mesh.nv))
+    assert host.iterations == r1.iterations
+    assert np.array_equal(host.x, r1.x.cpu().numpy())
+    capped = pkg.pcg_solve(g, d[0], d[1], d[2], idx, b, max_iter=5)
+    assert capped.iterations == 5 and not capped.converged
