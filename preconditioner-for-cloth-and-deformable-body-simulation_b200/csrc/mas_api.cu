@@ -73,7 +73,7 @@ static void free_all(Context* c)
 	release(c->scanTotal); release(c->coarseTables);
 	release(c->diagIn); release(c->offdiagIn); release(c->rangesIn); release(c->efIn); release(c->eeIn); release(c->vfIn);
 	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
-	release(c->coarseAcc); release(c->packedInv);
+	release(c->coarseAcc); release(c->packedInv); release(c->posTab);
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
 	release(c->pcgR); release(c->pcgZ); release(c->pcgP); release(c->pcgAp); release(c->pcgB); release(c->pcgX);
 	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);

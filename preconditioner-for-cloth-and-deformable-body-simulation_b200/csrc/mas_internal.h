@@ -138,6 +138,7 @@ struct Context
 	DevBuf<double> coarseAcc;            // exchange buffer: [nCoarseBlocks][96*96] dense + [nCoarseNodes][9] carry
 	size_t coarseAccCount = 0;
 	DevBuf<float> packedInv;             // [nBlocks][kTri]
+	DevBuf<unsigned short> posTab;       // packed positions of the inversion kernel's register-tile outputs
 
 	// ---- apply-time state
 	DevBuf<float4> coarseR, coarseZ, coarseZsum;  // indexed by node - nVC
