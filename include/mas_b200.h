@@ -66,7 +66,8 @@ enum
 	/* 0 (default): reproduce SeSchwarzPreconditioner.cpp:1710 — with 5 levels the top level is
 	 * solved but never prolonged.  1: prolong every level. */
 	MAS_OPT_PROLONG_ALL_LEVELS = 0,
-	/* apply kernel variant: 0 = default (best measured), see DESIGN.md */
+	/* per-mille of the fine domains that the apply graph solves CONCURRENTLY with the coarse-level chain
+	 * (0 = strictly sequential launches; default 200) */
 	MAS_OPT_APPLY_VARIANT = 1,
 	/* 1 (default): capture the apply launch sequence in a CUDA graph */
 	MAS_OPT_USE_GRAPH = 2,

@@ -104,6 +104,16 @@ int mas_create(mas_handle_t* out, int device)
 	cudaEventCreate(&c->evAp1);
 	cudaEventCreate(&c->evF0);
 	cudaEventCreate(&c->evF1);
+	cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->evHead, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->evCoarse, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->evTail, cudaEventDisableTiming);
+	{
+		int prLow = 0, prHigh = 0;
+		cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
+		cudaStreamCreateWithPriority(&c->sideA, cudaStreamNonBlocking, prLow);
+		cudaStreamCreateWithPriority(&c->sideB, cudaStreamNonBlocking, prLow);
+	}
 	*out = c;
 	return MAS_OK;
 }
@@ -120,6 +130,12 @@ int mas_destroy(mas_handle_t h)
 	if (h->evAp1) cudaEventDestroy(h->evAp1);
 	if (h->evF0) cudaEventDestroy(h->evF0);
 	if (h->evF1) cudaEventDestroy(h->evF1);
+	if (h->evFork) cudaEventDestroy(h->evFork);
+	if (h->evHead) cudaEventDestroy(h->evHead);
+	if (h->evCoarse) cudaEventDestroy(h->evCoarse);
+	if (h->evTail) cudaEventDestroy(h->evTail);
+	if (h->sideA) cudaStreamDestroy(h->sideA);
+	if (h->sideB) cudaStreamDestroy(h->sideB);
 	delete h;
 	return MAS_OK;
 }
@@ -281,16 +297,19 @@ static int run_apply_device(Context* c, const float4* r, float4* z)
 	if (!c->applyGraph || c->graphR != (const float*)r || c->graphZ != (float*)z)
 	{
 		drop_graph(c);
+		// the capture origin carries the latency-bound coarse chain: highest priority, so that its CTAs are dispatched ahead of
+		// the queued fine-level CTAs of the concurrent branch (kernel nodes inherit the capturing stream's priority)
 		cudaStream_t cap;
-		MAS_CUDA(c, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+		int prLow = 0, prHigh = 0;
+		MAS_CUDA(c, cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+		MAS_CUDA(c, cudaStreamCreateWithPriority(&cap, cudaStreamNonBlocking, prHigh));
 		cudaStream_t saved = c->stream;
 		c->stream = cap;
 		c->applyLaunches = 0;
 		cudaGraph_t graph = nullptr;
 		int rc = MAS_OK;
 		if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
-		if (rc == MAS_OK) rc = apply_begin(c, r);
-		if (rc == MAS_OK) rc = apply_end(c, r, z);
+		if (rc == MAS_OK) rc = apply_forked(c, r, z, cap);
 		cudaError_t e = cudaStreamEndCapture(cap, &graph);
 		c->stream = saved;
 		if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;

@@ -2,14 +2,18 @@
 // Replaces Preconditioning (SeSchwarzPreconditioner.cpp:100-110): the two memsets (102-103),
 // BuildResidualHierarchy (1548-1598), SchwarzLocalXSym (1600-1696) and CollectFinalZ (1698-1719).
 //
-// Launch sequence (captured once in a CUDA graph):
-//   1 restrict_fine     r (original order) -> level-1 residuals; level 0 is never materialised
-//   2 restrict_coarse   level l -> l+1, one launch per level (tiny)
-//   3 solve_coarse      Z_l = inv_l * R_l for every block of levels >= 1
-//   4 prolong_sum       per level-1 node: Z_1 + Z_2[parent] + ... (what CollectFinalZ adds to each of its vertices)
-//   5 solve_fine        gathers r again (L2 resident), multiplies by the packed level-0 inverse, adds the level-1
-//                       sum of step 4 and scatters z straight to original order
-// Step 5 moves 97 % of the bytes: 18,624 B of packed inverse per 32 vertices against 32 x (16+16) B of r/z,
+// Kernels:
+//   restrict_fine   r (original order) -> level-1 residuals; level 0 is never materialised
+//   restrict_l1     level 1 -> 2;  restrict_top: one CTA walks level 2 -> 3 -> ... (a few thousand nodes)
+//   solve_coarse    Z_l = inv_l * R_l for every block of levels >= 1, four warps per block (latency-bound)
+//   prolong_sum     per level-1 node: Z_1 + Z_2[parent] + ... (what CollectFinalZ adds to each of its vertices)
+//   solve_fine      gathers r again (L2 resident), multiplies by the packed level-0 inverse, adds the level-1 sum
+//                   and scatters z straight to original order
+//   add_coarse      z += level-1 sum, for the fine banks that were solved before the coarse levels finished
+// Captured once as a CUDA graph with two branches: the coarse chain (restrict_fine -> restrict_l1 -> restrict_top -> solve_coarse -> prolong_sum, ~3 % of
+// the bytes but latency-bound) runs CONCURRENTLY with solve_fine over the first part of the fine banks (which cannot add
+// the coarse part yet; add_coarse does that afterwards), then solve_fine with the fused addition runs over the rest.
+// solve_fine moves 97 % of the bytes: 18,624 B of packed inverse per 32 vertices against 32 x (16+16) B of r/z,
 // i.e. ~1 FLOP per byte, HBM-bound.  One warp owns one domain; lane i owns node i (3 rows).  The packed layout
 // (mas_internal.h) makes every load a fully coalesced 512-byte LDG.128 per warp; the symmetric half of each
 // 3x3 block is applied through two warp shuffles (x of the column node in, B^T x back out), so each matrix
@@ -176,36 +180,139 @@ __global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const floa
 	group_sum_store(key, val, lane, coarseR, nVC);
 }
 
-// BuildResidualHierarchy, level l -> l+1 for l >= 1 (cpp:1577-1591)
-__global__ void __launch_bounds__(kApplyThreads) restrict_coarse_kernel(const int* __restrict__ goingNext, int begin, int count,
-	int nVC, float4* __restrict__ coarseR)
+// One 32-node group of coarse nodes [begin + 32*bank, ...): sum R over the nodes that share a parent and store it
+// (BuildResidualHierarchy level l -> l+1, cpp:1577-1591)
+__device__ __forceinline__ void restrict_bank(const int* __restrict__ goingNext, int begin, int count, int bank, int nVC,
+	float4* __restrict__ coarseR, int lane, const float4 rv)
 {
-	const int lane = threadIdx.x & 31;
-	const int bank = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	if (bank * 32 >= count) return;
 	const int local = bank * 32 + lane;
 	int key = -1;
 	Vec3 val = { 0.f, 0.f, 0.f };
 	if (local < count)
 	{
-		const float4 rv = coarseR[begin + local - nVC];
 		val.x = rv.x; val.y = rv.y; val.z = rv.z;
 		key = goingNext[begin + local];
 	}
 	group_sum_store(key, val, lane, coarseR, nVC);
 }
 
-// SchwarzLocalXSym on the blocks of levels >= 1 (cpp:1600-1696)
-__global__ void __launch_bounds__(kApplyThreads) solve_coarse_kernel(const float* __restrict__ packed, int nBlocks,
-	const float4* __restrict__ coarseR, float4* __restrict__ coarseZ)
+// BuildResidualHierarchy, level 1 -> 2 (cpp:1577-1591): one warp per 32 level-1 nodes
+__global__ void __launch_bounds__(kApplyThreads) restrict_l1_kernel(const int* __restrict__ goingNext, int begin, int count,
+	int nVC, float4* __restrict__ coarseR)
 {
 	const int lane = threadIdx.x & 31;
-	const int blk = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	if (blk >= nBlocks) return;
+	const int bank = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (bank * 32 >= count) return;
+	const int local = bank * 32 + lane;
+	float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (local < count) rv = coarseR[begin - nVC + local];
+	restrict_bank(goingNext, begin, count, bank, nVC, coarseR, lane, rv);
+}
+
+// Levels >= 2 hold a few thousand nodes at most: one CTA walks the remaining restrictions level by level.
+struct TopArgs
+{
+	int numLevel, nVC;
+	int count[kMaxLevel + 1], begin[kMaxLevel + 1];
+};
+constexpr int kTopThreads = 1024;
+__global__ void __launch_bounds__(kTopThreads) restrict_top_kernel(const int* __restrict__ goingNext, TopArgs a, float4* __restrict__ coarseR)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = kTopThreads / 32;
+	for (int level = 2; level + 1 < a.numLevel; ++level)
+	{
+		const int banks = (a.count[level] + 31) >> 5;
+		for (int bank = warp; bank < banks; bank += nWarps)
+		{
+			const int local = bank * 32 + lane;
+			float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (local < a.count[level]) rv = coarseR[a.begin[level] - a.nVC + local];
+			restrict_bank(goingNext, a.begin[level], a.count[level], bank, a.nVC, coarseR, lane, rv);
+		}
+		__threadfence_block();
+		__syncthreads();
+	}
+}
+
+// One quarter of a packed block (the same four register batches solve_domain_ldg walks through one after the other):
+// Q = 0,1,2: cyclic block diagonals 4Q+1 .. 4Q+4;  Q = 3: diagonals 13..15, the diagonal blocks and the half diagonal.
+template <int Q>
+__device__ __forceinline__ Vec3 solve_quarter(const float* __restrict__ blk, int lane, const Vec3 x)
+{
+	const float4* p4 = reinterpret_cast<const float4*>(blk) + lane;
+	Vec3 y = { 0.f, 0.f, 0.f };
+	float4 buf[9];
+	if (Q < 3)
+	{
+#pragma unroll
+		for (int q = 0; q < 9; ++q) buf[q] = ldg_stream4(p4 + 32 * (9 * Q + q));
+		const float* m = reinterpret_cast<const float*>(buf);
+#pragma unroll
+		for (int dd = 0; dd < 4; ++dd) apply_block(m + 9 * dd, 4 * Q + 1 + dd, lane, x, y);
+		return y;
+	}
+#pragma unroll
+	for (int q = 0; q < 8; ++q) buf[q] = ldg_stream4(p4 + 32 * (27 + q));
+	const float dTail = ldg_stream1(blk + kTailBase + lane);
+	float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0;
+	float h8 = 0.f;
+	if (lane < 16)
+	{
+		const float4* ph = reinterpret_cast<const float4*>(blk + kHalfBase) + lane;
+		h0 = ldg_stream4(ph);
+		h1 = ldg_stream4(ph + 16);
+		h8 = ldg_stream1(blk + kHalfTail + lane);
+	}
+	const float* m = reinterpret_cast<const float*>(buf);
+#pragma unroll
+	for (int dd = 0; dd < 3; ++dd) apply_block(m + 9 * dd, 13 + dd, lane, x, y);
+	const float d0 = m[27], d1 = m[28], d2 = m[29], d3 = m[30], d4 = m[31], d5 = dTail;
+	y.x = fmaf(d0, x.x, fmaf(d1, x.y, fmaf(d3, x.z, y.x)));
+	y.y = fmaf(d1, x.x, fmaf(d2, x.y, fmaf(d4, x.z, y.y)));
+	y.z = fmaf(d3, x.x, fmaf(d4, x.y, fmaf(d5, x.z, y.z)));
+	const float b[9] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h8 };
+	const int peer = lane ^ 16;
+	const float xjx = __shfl_sync(kFull, x.x, peer), xjy = __shfl_sync(kFull, x.y, peer), xjz = __shfl_sync(kFull, x.z, peer);
+	float tx = 0.f, ty = 0.f, tz = 0.f;
+	if (lane < 16)
+	{
+		y.x = fmaf(b[0], xjx, fmaf(b[1], xjy, fmaf(b[2], xjz, y.x)));
+		y.y = fmaf(b[3], xjx, fmaf(b[4], xjy, fmaf(b[5], xjz, y.y)));
+		y.z = fmaf(b[6], xjx, fmaf(b[7], xjy, fmaf(b[8], xjz, y.z)));
+		tx = fmaf(b[0], x.x, fmaf(b[3], x.y, b[6] * x.z));
+		ty = fmaf(b[1], x.x, fmaf(b[4], x.y, b[7] * x.z));
+		tz = fmaf(b[2], x.x, fmaf(b[5], x.y, b[8] * x.z));
+	}
+	const float rx = __shfl_sync(kFull, tx, peer), ry = __shfl_sync(kFull, ty, peer), rz = __shfl_sync(kFull, tz, peer);
+	if (lane >= 16) { y.x += rx; y.y += ry; y.z += rz; }
+	return y;
+}
+
+// SchwarzLocalXSym on the blocks of levels >= 1 (cpp:1600-1696).  There are few of them (3 % of all blocks), so the kernel
+// is latency-bound: FOUR warps share a block, each streaming one quarter of it in a single batch of loads, and the four
+// partial products are added in a fixed order.
+__global__ void __launch_bounds__(128) solve_coarse_kernel(const float* __restrict__ packed, const float4* __restrict__ coarseR,
+	float4* __restrict__ coarseZ)
+{
+	__shared__ float part[3][32][3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int blk = blockIdx.x;
 	const float4 rv = coarseR[blk * 32 + lane];
 	const Vec3 x = { rv.x, rv.y, rv.z };
-	const Vec3 y = solve_domain_ldg(packed + (size_t)blk * kTri, lane, x);
-	coarseZ[blk * 32 + lane] = make_float4(y.x, y.y, y.z, 0.f);
+	const float* base = packed + (size_t)blk * kTri;
+	Vec3 y;
+	if (warp == 0) y = solve_quarter<0>(base, lane, x);
+	else if (warp == 1) y = solve_quarter<1>(base, lane, x);
+	else if (warp == 2) y = solve_quarter<2>(base, lane, x);
+	else y = solve_quarter<3>(base, lane, x);
+	if (warp > 0) { part[warp - 1][lane][0] = y.x; part[warp - 1][lane][1] = y.y; part[warp - 1][lane][2] = y.z; }
+	__syncthreads();
+	if (warp == 0)
+	{
+#pragma unroll
+		for (int w = 0; w < 3; ++w) { y.x += part[w][lane][0]; y.y += part[w][lane][1]; y.z += part[w][lane][2]; }
+		coarseZ[blk * 32 + lane] = make_float4(y.x, y.y, y.z, 0.f);
+	}
 }
 
 // what CollectFinalZ (cpp:1698-1719) adds to every vertex below a level-1 node: Z_1 + Z_2[parent] + ...
@@ -225,14 +332,14 @@ __global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int
 	zsum[i] = make_float4(z.x, z.y, z.z, 0.f);
 }
 
-// SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ
-__global__ void __launch_bounds__(kApplyThreads) solve_fine_kernel(const float* __restrict__ packed,
+// SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ.
+// addCoarse = 0: the coarse levels are not ready (or absent); z holds the level-0 part only.
+__global__ void __launch_bounds__(kApplyThreads, 8) solve_fine_kernel(const float* __restrict__ packed,
 	const float4* __restrict__ r, const int* __restrict__ s2o, const int* __restrict__ goingNext,
-	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int addCoarse, float4* __restrict__ z)
+	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int packedBankBase, int addCoarse, float4* __restrict__ z)
 {
 	const int lane = threadIdx.x & 31;
-	const int local = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	const int bank = bankBegin + local;
+	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
 	if (bank >= bankEnd) return;
 	const int v = bank * 32 + lane;
 	const bool live = v < nv;
@@ -245,7 +352,7 @@ __global__ void __launch_bounds__(kApplyThreads) solve_fine_kernel(const float* 
 		x.x = rv.x; x.y = rv.y; x.z = rv.z;
 		if (addCoarse) parent = goingNext[v];
 	}
-	Vec3 y = solve_domain_ldg(packed + (size_t)local * kTri, lane, x);
+	Vec3 y = solve_domain_ldg(packed + (size_t)(bank - packedBankBase) * kTri, lane, x);
 	if (live)
 	{
 		if (addCoarse)
@@ -255,6 +362,19 @@ __global__ void __launch_bounds__(kApplyThreads) solve_fine_kernel(const float* 
 		}
 		z[ov] = make_float4(y.x, y.y, y.z, 0.f);
 	}
+}
+
+// z += prolonged coarse solutions for the fine banks solved with addCoarse = 0
+__global__ void add_coarse_kernel(const int* __restrict__ s2o, const int* __restrict__ goingNext, const float4* __restrict__ zsum,
+	int vBegin, int vEnd, int nVC, float4* __restrict__ z)
+{
+	const int v = vBegin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= vEnd) return;
+	const int ov = s2o[v];
+	const float4 c = zsum[goingNext[v] - nVC];
+	float4 y = z[ov];
+	y.x += c.x; y.y += c.y; y.z += c.z;
+	z[ov] = make_float4(y.x, y.y, y.z, 0.f);
 }
 
 }  // namespace
@@ -283,35 +403,105 @@ int apply_begin(Context* c, const float4* r)
 	return MAS_OK;
 }
 
+// coarse levels: needs the complete level-1 residuals in coarseR (after the exchange when world > 1)
+static int launch_coarse(Context* c, cudaStream_t st)
+{
+	if (c->numLevel < 2) return MAS_OK;
+	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
+	const int nCoarseBlocks = c->nCoarseNodes / 32;
+	if (c->numLevel > 2)
+	{
+		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, c->coarseR.p);
+		c->applyLaunches += 1;
+	}
+	if (c->numLevel > 3)
+	{
+		TopArgs a;
+		a.numLevel = c->numLevel; a.nVC = c->nVC;
+		for (int l = 0; l <= kMaxLevel; ++l) { a.count[l] = 0; a.begin[l] = 0; }
+		for (int l = 1; l <= c->numLevel; ++l) { a.count[l] = c->levelSize[l][0]; a.begin[l] = c->levelSize[l][1]; }
+		restrict_top_kernel<<<1, kTopThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p);
+		c->applyLaunches += 1;
+	}
+	solve_coarse_kernel<<<nCoarseBlocks, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
+		c->coarseZ.p);
+	c->applyLaunches += 1;
+	prolong_sum_kernel<<<cdiv(cnt1, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, begin1, cnt1, c->nVC, prolonged_top(c) - 2, c->coarseZsum.p);
+	c->applyLaunches += 1;
+	return MAS_OK;
+}
+
+static void launch_fine(Context* c, cudaStream_t st, const float4* r, float4* z, int bankBegin, int bankEnd, int addCoarse)
+{
+	if (bankEnd <= bankBegin) return;
+	solve_fine_kernel<<<cdiv(bankEnd - bankBegin, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p, r, c->s2o.p, c->goingNext.p,
+		c->coarseZsum.p, c->nv, c->nVC, bankBegin, bankEnd, c->ownFineBegin, addCoarse, z);
+	c->applyLaunches += 1;
+}
+
 int apply_end(Context* c, const float4* r, float4* z)
 {
 	cudaStream_t st = c->stream;
-	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
-	const int nCoarseBlocks = c->nCoarseNodes / 32;
-	const int top = prolonged_top(c);
-	if (c->numLevel >= 2)
-	{
-		for (int level = 1; level + 1 < c->numLevel; ++level)
-		{
-			const int cnt = c->levelSize[level][0], begin = c->levelSize[level][1];
-			restrict_coarse_kernel<<<cdiv(cdiv(cnt, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin, cnt, c->nVC, c->coarseR.p);
-			c->applyLaunches += 1;
-		}
-		solve_coarse_kernel<<<cdiv(nCoarseBlocks, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p + (size_t)ownBanks * kTri,
-			nCoarseBlocks, c->coarseR.p, c->coarseZ.p);
-		const int cnt1 = c->levelSize[1][0];
-		prolong_sum_kernel<<<cdiv(cnt1, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, c->levelSize[1][1], cnt1, c->nVC, top - 2,
-			c->coarseZsum.p);
-		c->applyLaunches += 2;
-	}
-	if (ownBanks > 0)
+	if (int rc = launch_coarse(c, st)) return rc;
+	if (c->ownFineEnd > c->ownFineBegin)
 	{
 		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evF0, st));
-		solve_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(c->packedInv.p, r, c->s2o.p, c->goingNext.p,
-			c->coarseZsum.p, c->nv, c->nVC, c->ownFineBegin, c->ownFineEnd, top >= 2 ? 1 : 0, z);
+		launch_fine(c, st, r, z, c->ownFineBegin, c->ownFineEnd, prolonged_top(c) >= 2 ? 1 : 0);
 		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evF1, st));
-		c->applyLaunches += 1;
 	}
+	MAS_CUDA(c, cudaGetLastError());
+	return MAS_OK;
+}
+
+// Whole apply as a two-branch capture (single-GPU graph path).  `st` is the capturing origin stream; side streams and
+// events belong to the context.  headBanks fine banks are solved concurrently with the coarse chain.
+int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
+{
+	const int top = prolonged_top(c);
+	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
+	int head = 0;
+	if (top >= 2 && c->optApplyVariant > 0)
+	{
+		head = (int)((long long)ownBanks * c->optApplyVariant / 1000);
+		head = head / kWarpsPerCta * kWarpsPerCta;
+		if (head > ownBanks) head = ownBanks;
+	}
+	if (head == 0)
+	{
+		cudaStream_t saved = c->stream;
+		c->stream = st;
+		int rc = apply_begin(c, r);
+		if (rc == MAS_OK) rc = apply_end(c, r, z);
+		c->stream = saved;
+		return rc;
+	}
+	const int b0 = c->ownFineBegin, b1 = b0 + head, b2 = c->ownFineEnd;
+	MAS_CUDA(c, cudaEventRecord(c->evFork, st));
+	MAS_CUDA(c, cudaStreamWaitEvent(c->sideA, c->evFork, 0));
+	launch_fine(c, c->sideA, r, z, b0, b1, 0);                      // level-0 part only, no coarse data needed
+	MAS_CUDA(c, cudaEventRecord(c->evHead, c->sideA));
+	{
+		cudaStream_t saved = c->stream;
+		c->stream = st;
+		int rc = apply_begin(c, r);
+		if (rc == MAS_OK) rc = launch_coarse(c, st);
+		c->stream = saved;
+		if (rc != MAS_OK) return rc;
+	}
+	MAS_CUDA(c, cudaEventRecord(c->evCoarse, st));
+	MAS_CUDA(c, cudaStreamWaitEvent(c->sideB, c->evCoarse, 0));
+	launch_fine(c, c->sideB, r, z, b1, b2, 1);
+	MAS_CUDA(c, cudaEventRecord(c->evTail, c->sideB));
+	MAS_CUDA(c, cudaStreamWaitEvent(st, c->evHead, 0));
+	{
+		const int vBegin = b0 * 32, vEnd = b1 * 32 < c->nv ? b1 * 32 : c->nv;
+		if (vEnd > vBegin)
+		{
+			add_coarse_kernel<<<cdiv(vEnd - vBegin, 256), 256, 0, st>>>(c->s2o.p, c->goingNext.p, c->coarseZsum.p, vBegin, vEnd, c->nVC, z);
+			c->applyLaunches += 1;
+		}
+	}
+	MAS_CUDA(c, cudaStreamWaitEvent(st, c->evTail, 0));
 	MAS_CUDA(c, cudaGetLastError());
 	return MAS_OK;
 }

@@ -91,7 +91,7 @@ struct Context
 	cudaStream_t stream = nullptr;
 	std::string err;
 	int optProlongAll = 0;
-	int optApplyVariant = 0;
+	int optApplyVariant = 200;   // per-mille of the fine banks solved concurrently with the coarse chain (graph path)
 	int optUseGraph = 1;
 	int optTimeKernels = 0;
 	int rank = 0, world = 1;
@@ -164,6 +164,8 @@ struct Context
 	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
 	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)
 	cudaEvent_t evF0 = nullptr, evF1 = nullptr;    // level-0 solve kernel (timed mode)
+	cudaStream_t sideA = nullptr, sideB = nullptr; // branches of the apply graph
+	cudaEvent_t evFork = nullptr, evHead = nullptr, evCoarse = nullptr, evTail = nullptr;
 	float lastApplyMs = 0.f, lastPrepareMs = 0.f;
 };
 
@@ -206,6 +208,7 @@ int assemble_and_invert_end(Context* c);                                        
 int unpack_dense_inverse(Context* c, int block, float* hostOut);                                  // mas_assemble.cu
 int apply_begin(Context* c, const float4* r);                                                     // mas_apply.cu
 int apply_end(Context* c, const float4* r, float4* z);                                            // mas_apply.cu
+int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st);                        // mas_apply.cu
 int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges, const int* idx, const float4* b, float4* x,
 	float relTol, int maxIter, int usePrecond, int* itersOut, float* relResOut);                  // mas_pcg.cu
 

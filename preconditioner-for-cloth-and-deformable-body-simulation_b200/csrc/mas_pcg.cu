@@ -280,7 +280,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(diag, off, ranges, idx, p, Ap, nv, pA, state);
 		axpy_rr_kernel<<<grid, kPcgThreads, 0, cap>>>(x, r, p, Ap, nv, pA, nPart, pRR, state);
 		c->applyLaunches = 0;
-		rc = precondition();
+		if (usePrecond) rc = apply_forked(c, r, z, cap);   // coarse chain concurrent with the head of the fine solve
 		dot_kernel<<<grid, kPcgThreads, 0, cap>>>(r, z, nv, pRZ, state);
 		update_p_kernel<<<grid, kPcgThreads, 0, cap>>>(p, z, nv, pRZ, pRR, nPart, tol2, 1, state);
 	}

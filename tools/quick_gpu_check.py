@@ -15,7 +15,8 @@ for i in range(3):
     g.PreparePreconditioner(d[0], d[1], d[2])
     torch.cuda.synchronize(); print("prepare wall ms", (time.time() - t) * 1e3, "device ms", g.timing_ms(0))
 r = torch.from_numpy(S.residual(mesh.nv)).cuda(); z = torch.empty_like(r)
-for variant in (0,):
+for variant in [int(x) for x in os.environ.get('MAS_VARIANTS', '200').split(',')]:
+    g.set_option(1, variant)
     for _ in range(5): g.Preconditioning(z, r)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
