@@ -204,6 +204,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -234,6 +235,14 @@ def run_ours(args):
             dist.all_reduce(g.exchange_tensor(0))
             g.prepare_end()
 
+    if args.variant is not None:
+        g.set_option(1, args.variant)
+    p2p = False
+    if world > 1:
+        drv = pkg.partition.ShardedSchwarzPreconditioner(g)
+        p2p = drv.attach_peers() and not args.nccl_exchange
+        if not p2p:
+            drv.p2p = False
     prepare()
     setup_wall = []
     for _ in range(3):
@@ -250,8 +259,8 @@ def run_ours(args):
     exch = g.exchange_tensor(1) if world > 1 else None
 
     def step():
-        if world == 1:
-            g.Preconditioning(z, r)
+        if world == 1 or p2p:
+            g.Preconditioning(z, r)          # one CUDA graph per rank; sharded ranks exchange over peer memory on the device
         else:
             g.apply_begin(r)
             dist.all_reduce(exch)
@@ -300,7 +309,7 @@ def run_ours(args):
     r_stage, z_stage = torch.empty_like(r), torch.empty_like(r)
 
     def e2e_step():
-        if world == 1:
+        if world == 1 or p2p:
             g.Preconditioning(z_h, r_h)          # mas_apply(MAS_MEM_HOST): cudaMemcpyAsync in, graph, cudaMemcpyAsync out, sync
         else:
             r_stage.copy_(r_h, non_blocking=True)
@@ -395,7 +404,9 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[args.config], "nv": nv, "levels": lv, "blocks": n_blocks,
                    "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step vs 126 MB L2",
                    "timing": "CUDA events on the launching stream, max over ranks",
-                   "parallelism": f"morton-sharded x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"morton-sharded x{world}, " + ("peer-memory exchange fused into the restriction kernel (NVLink)"
+                                                                      if p2p else "NCCL all-reduce of coarse residuals"))
+                   if world > 1 else "single GPU"},
         "setup_ms": setup_ms, "setup_device_ms": setup_device_ms,
         "e2e": {"value": e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv, "d2h_bytes_per_step": 16 * nv,
                 "steps": e2e_steps},
@@ -416,6 +427,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="index into BASELINE.json configs (default 2: 1M-vertex cloth)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
+    ap.add_argument("--variant", type=int, default=None, help="MAS_OPT_APPLY_VARIANT override (development sweeps)")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -66,8 +66,9 @@ enum
 	/* 0 (default): reproduce SeSchwarzPreconditioner.cpp:1710 — with 5 levels the top level is
 	 * solved but never prolonged.  1: prolong every level. */
 	MAS_OPT_PROLONG_ALL_LEVELS = 0,
-	/* per-mille of the fine domains that the apply graph solves CONCURRENTLY with the coarse-level chain
-	 * (0 = strictly sequential launches; default 200) */
+	/* share of the owned fine domains that the apply graph solves CONCURRENTLY with the coarse-level chain:
+	 * -1 (default) sized automatically to the chain's duration, 0 = strictly sequential launches, >0 = per-mille
+	 *  */
 	MAS_OPT_APPLY_VARIANT = 1,
 	/* 1 (default): capture the apply launch sequence in a CUDA graph */
 	MAS_OPT_USE_GRAPH = 2,
@@ -91,7 +92,8 @@ enum
 	MAS_INT_OWNED_BLOCK_END = 9,
 	MAS_INT_PREPARE_LAUNCHES = 10, /* kernels launched by the last mas_prepare */
 	MAS_INT_PCG_LAUNCHES_PER_ITER = 11, /* kernels per iteration of the last mas_pcg_solve (its own 4 + the apply's) */
-	MAS_INT_PCG_CONVERGED = 12     /* 1 if the last mas_pcg_solve met its tolerance */
+	MAS_INT_PCG_CONVERGED = 12,    /* 1 if the last mas_pcg_solve met its tolerance */
+	MAS_INT_PEER_ERROR = 13        /* 1 if a peer-memory wait ever timed out (a rank stopped publishing) */
 };
 
 /* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */
@@ -152,6 +154,19 @@ int mas_apply_begin(mas_handle_t h, const float* residual, int mem);
 int mas_apply_end(mas_handle_t h, float* z, int mem);
 /* which: 0 = prepare exchange (double), 1 = apply exchange (float). Returns a DEVICE pointer + element count. */
 int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* count);
+
+/* Multi-GPU apply exchange over peer memory (NVLink / NVSwitch), replacing the all-reduce of mas_apply_begin/_end:
+ * every rank's level-0 restriction kernel stores its level-1 residuals straight into an arena of every other rank and
+ * raises a flag there; the coarse levels wait on those flags on the device.  With the peers attached, mas_apply() on
+ * a sharded context is again ONE call (one CUDA graph, no host synchronisation, no NCCL call per apply).
+ *   mas_peer_export : 64-byte cudaIpcMemHandle_t of this rank's arena, to be sent to the other PROCESSES
+ *   mas_peer_local  : the arena's device pointer, for other contexts of THIS process
+ *   mas_peer_attach : handles = world x 64 bytes in rank order (or NULL), pointers = world device pointers (or NULL);
+ *                     for each peer the pointer is used if non-NULL, else the handle is opened.
+ * Call after mas_allocate on every rank (the arena is sized there).  Setup still uses mas_prepare_begin/_end. */
+int mas_peer_export(mas_handle_t h, void* handle_out_64);
+int mas_peer_local(mas_handle_t h, void** arena_out);
+int mas_peer_attach(mas_handle_t h, const void* handles, void* const* pointers);
 
 /* Caller-side harness (the reference ships no solver): preconditioned conjugate gradients for A x = b with
  * everything resident on the GPU.  A is given exactly as PreparePreconditioner receives it (original vertex order):

@@ -60,9 +60,22 @@ static void drop_graph(Context* c)
 	c->graphZ = nullptr;
 }
 
+static void close_peers(Context* c)
+{
+	for (int q = 0; q < 16; ++q)
+	{
+		if (c->peerOpened[q] && c->peerArena[q]) cudaIpcCloseMemHandle(c->peerArena[q]);
+		c->peerOpened[q] = false;
+		c->peerArena[q] = nullptr;
+	}
+	c->p2p = false;
+}
+
 static void free_all(Context* c)
 {
 	drop_graph(c);
+	close_peers(c);
+	release(c->arena);
 	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
 	release(c->aabb); release(c->code); release(c->codeSorted); release(c->s2o); release(c->o2s); release(c->iota);
 	release(c->adjStart); release(c->adjIdx); release(c->cubTemp);
@@ -215,6 +228,16 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 	c->ownFineBegin = (int)((long long)nFine * c->rank / c->world);
 	c->ownFineEnd = (int)((long long)nFine * (c->rank + 1) / c->world);
 
+	if (c->world > 1)
+	{
+		// peer-writable arena: two receive buffers for the coarse residuals + control words.  Coarse nodes number about
+		// nv/31 on meshes whose banks stay connected; 1/8 of the vertices (+ slack) is the capacity, checked in mas_prepare.
+		c->arenaCap = (size_t)c->nVC / 8 + 8192;
+		const size_t bytes = 2 * sizeof(float4) * c->arenaCap + 256;
+		if (int rc = reserve(c, c->arena, bytes)) return rc;
+		MAS_CUDA(c, cudaMemsetAsync(c->arena.p, 0, bytes, c->stream));
+		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
 	if (int rc = order_vertices(c, dPos, dStarts, dIdx)) return rc;
 	c->allocated = true;
 	c->prepared = false;
@@ -251,6 +274,8 @@ int mas_prepare_begin(mas_handle_t h, const float* diagonal, const float* csrOff
 	if (int rc = build_stencils(c, dEf, dEe, dVf, efTotal, eeTotal, vfTotal)) return rc;
 	if (int rc = build_hierarchy(c)) return rc;
 
+	if (c->p2p && (size_t)c->nCoarseNodes > c->arenaCap)
+		return fail(c, MAS_ERR_UNSUPPORTED, "coarse hierarchy larger than the peer arena: use the begin/exchange/end protocol");
 	// apply-side buffers, sized from the actual hierarchy; padding slots stay zero for the lifetime of this setup
 	const size_t nc = (size_t)(c->nCoarseNodes > 0 ? c->nCoarseNodes : 1);
 	if (int rc = reserve(c, c->coarseR, nc)) return rc;
@@ -285,7 +310,7 @@ int mas_prepare(mas_handle_t h, const float* diagonal, const float* csrOffDiagon
 
 static int run_apply_device(Context* c, const float4* r, float4* z)
 {
-	if (c->world > 1 || !c->optUseGraph || c->optTimeKernels)
+	if ((c->world > 1 && !c->p2p) || !c->optUseGraph || c->optTimeKernels)
 	{
 		c->applyLaunches = 0;
 		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evAp0, c->stream));
@@ -329,6 +354,8 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	if (!h || !z || !residual) return MAS_ERR_INVALID;
 	Context* c = h;
 	if (!c->prepared) return fail(c, MAS_ERR_INVALID, "mas_prepare first");
+	if (c->world > 1 && !c->p2p)
+		return fail(c, MAS_ERR_INVALID, "sharded context: attach the peers (mas_peer_attach) or use mas_apply_begin / exchange / mas_apply_end");
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
@@ -402,6 +429,71 @@ int mas_exchange_buffer(mas_handle_t h, int which, void** device_ptr, size_t* co
 	return MAS_ERR_INVALID;
 }
 
+int mas_peer_export(mas_handle_t h, void* handle_out_64)
+{
+	if (!h || !handle_out_64) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (c->world < 2 || !c->arena.p) return fail(c, MAS_ERR_INVALID, "mas_set_partition(world > 1) and mas_allocate first");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t hd;
+	MAS_CUDA(c, cudaIpcGetMemHandle(&hd, c->arena.p));
+	std::memcpy(handle_out_64, &hd, 64);
+	return MAS_OK;
+}
+
+int mas_peer_local(mas_handle_t h, void** arena_out)
+{
+	if (!h || !arena_out) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (c->world < 2 || !c->arena.p) return fail(c, MAS_ERR_INVALID, "mas_set_partition(world > 1) and mas_allocate first");
+	*arena_out = c->arena.p;
+	return MAS_OK;
+}
+
+int mas_peer_attach(mas_handle_t h, const void* handles, void* const* pointers)
+{
+	if (!h || (!handles && !pointers)) return MAS_ERR_INVALID;
+	Context* c = h;
+	if (c->world < 2 || !c->arena.p) return fail(c, MAS_ERR_INVALID, "mas_set_partition(world > 1) and mas_allocate first");
+	if (c->world > 16) return fail(c, MAS_ERR_UNSUPPORTED, "peer exchange supports up to 16 ranks");
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	drop_graph(c);
+	close_peers(c);
+	for (int q = 0; q < c->world; ++q)
+	{
+		if (q == c->rank) { c->peerArena[q] = c->arena.p; continue; }
+		if (pointers && pointers[q])
+		{
+			// another context of this process: make sure its device is peer-accessible
+			cudaPointerAttributes at;
+			MAS_CUDA(c, cudaPointerGetAttributes(&at, pointers[q]));
+			if (at.device != c->device)
+			{
+				cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { check(c, e, "cudaDeviceEnablePeerAccess"); close_peers(c); return MAS_ERR_CUDA; }
+				cudaGetLastError();
+			}
+			c->peerArena[q] = pointers[q];
+			continue;
+		}
+		if (!handles) { close_peers(c); return fail(c, MAS_ERR_INVALID, "no handle or pointer for a peer"); }
+		cudaIpcMemHandle_t hd;
+		std::memcpy(&hd, (const unsigned char*)handles + 64 * (size_t)q, 64);
+		void* p = nullptr;
+		if (!check(c, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) { close_peers(c); return MAS_ERR_CUDA; }
+		c->peerArena[q] = p;
+		c->peerOpened[q] = true;
+	}
+	if (c->prepared && (size_t)c->nCoarseNodes > c->arenaCap)
+	{
+		close_peers(c);
+		return fail(c, MAS_ERR_UNSUPPORTED, "coarse hierarchy larger than the peer arena");
+	}
+	c->p2p = true;
+	return MAS_OK;
+}
+
 int mas_get_int(mas_handle_t h, int key, long long* out)
 {
 	if (!h || !out) return MAS_ERR_INVALID;
@@ -421,6 +513,19 @@ int mas_get_int(mas_handle_t h, int key, long long* out)
 	case MAS_INT_PREPARE_LAUNCHES: *out = c->prepareLaunches; break;
 	case MAS_INT_PCG_LAUNCHES_PER_ITER: *out = c->pcgLaunchesPerIter; break;
 	case MAS_INT_PCG_CONVERGED: *out = c->pcgConverged; break;
+	case MAS_INT_PEER_ERROR:
+	{
+		*out = 0;
+		if (c->p2p)
+		{
+			unsigned v = 0;
+			const unsigned char* ctl = (const unsigned char*)c->arena.p + 2 * sizeof(float4) * c->arenaCap;
+			MAS_CUDA(c, cudaMemcpyAsync(&v, ctl + sizeof(unsigned) * (16 + 2), sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+			MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+			*out = v;
+		}
+		break;
+	}
 	default: return fail(c, MAS_ERR_INVALID, "unknown int key");
 	}
 	return MAS_OK;

@@ -139,7 +139,8 @@ __device__ __forceinline__ Vec3 solve_domain_ldg(const float* __restrict__ blk, 
 // Sum `val` over the lanes that share `key` (key < 0: lane takes no part) in a fixed butterfly order and let the
 // lowest lane of each group store it.  All children of a coarse node sit in one bank (clustering is per bank),
 // so a plain store is enough: no atomics, deterministic.
-__device__ __forceinline__ void group_sum_store(int key, Vec3 val, int lane, float4* __restrict__ out, int outBase)
+__device__ __forceinline__ void group_sum_store(int key, Vec3 val, int lane, float4* __restrict__ out, int outBase,
+	float4* __restrict__ out2 = nullptr)
 {
 	unsigned peers = __match_any_sync(kFull, key);
 	unsigned todo = __ballot_sync(kFull, key >= 0 && lane == __ffs(peers) - 1);  // one bit per group (its leader)
@@ -157,13 +158,19 @@ __device__ __forceinline__ void group_sum_store(int key, Vec3 val, int lane, flo
 			sy += __shfl_xor_sync(kFull, sy, off);
 			sz += __shfl_xor_sync(kFull, sz, off);
 		}
-		if (lane == leader) out[key - outBase] = make_float4(sx, sy, sz, 0.f);
+		if (lane == leader)
+		{
+			out[key - outBase] = make_float4(sx, sy, sz, 0.f);
+			if (out2) out2[key - outBase] = make_float4(sx, sy, sz, 0.f);
+		}
 	}
 }
 
-// BuildResidualHierarchy, level 0 -> 1 (cpp:1558-1574)
+// BuildResidualHierarchy, level 0 -> 1 (cpp:1558-1574).  `send` (sharded contexts with attached peers): second copy of the
+// results in this rank's peer-readable send buffer, selected by the parity of the next apply counter.
 __global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const float4* __restrict__ r, const int* __restrict__ s2o,
-	const int* __restrict__ goingNext, int nv, int nVC, int bankBegin, int bankEnd, float4* __restrict__ coarseR)
+	const int* __restrict__ goingNext, int nv, int nVC, int bankBegin, int bankEnd, float4* __restrict__ coarseR,
+	float4* __restrict__ send, unsigned long long sendCap, const unsigned* epoch)
 {
 	const int lane = threadIdx.x & 31;
 	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -177,7 +184,106 @@ __global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const floa
 		val.x = rv.x; val.y = rv.y; val.z = rv.z;
 		key = goingNext[v];
 	}
-	group_sum_store(key, val, lane, coarseR, nVC);
+	float4* second = nullptr;
+	if (send) second = send + (unsigned long long)((*reinterpret_cast<const volatile unsigned*>(epoch) + 1u) & 1u) * sendCap;
+	group_sum_store(key, val, lane, coarseR, nVC, second);
+}
+
+// ---- multi-GPU exchange over peer memory (NVLink) ---------------------------------------------------------------
+// Every rank owns an "arena" that its peers have mapped: two SEND buffers for its level-1 residuals (double-buffered by
+// the parity of the apply counter) and one arrival flag per rank.  The level-1 nodes a rank produces form one contiguous
+// range (ids follow the Morton order of the fine banks) and have no other producer, so the exchange is an all-gather
+// without a reduction, done as a PULL:
+//   restrict_fine    writes its residuals to the local coarseR and to the local send buffer (plain local stores);
+//   signal_peers     one warp stores the apply counter into every rank's flag slot (the payload was completed by the
+//                    previous kernel, so the flag store itself carries no fence);
+//   gather_peers     wait (load-acquire) until all ranks have published this apply, then read the foreign slices
+//                    straight out of the peers' send buffers over NVLink into the local coarseR.
+// No NCCL call, no host involvement, no remote stores of payload (a push variant needed a system-scope fence in every
+// storing CTA and cost 15-29 us per apply): the whole sharded apply stays one CUDA graph per rank.
+// Why two buffers are enough: a peer can only be one apply ahead of a rank it still has to hear from.
+constexpr int kMaxWorld = 16;
+struct PeerArgs
+{
+	float4* send[kMaxWorld];      // arena base of every rank (send buffer b at send[q] + b * cap)
+	unsigned* flags[kMaxWorld];   // flags array of every rank; slot [rank] is written by `rank`
+	int sliceBegin[kMaxWorld + 1];// level-1 slice (coarse index) produced by rank q: [sliceBegin[q], sliceBegin[q+1])
+	unsigned* epoch;              // local apply counter
+	unsigned* error;              // local sticky error flag (peer wait timed out)
+	unsigned long long cap;       // float4 elements per send buffer
+	int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// The residuals of this apply are complete in the local send buffer: they were written by the PREVIOUS kernel on this
+// stream, so they already sit in this GPU's L2 (the point of coherence for reads arriving over NVLink).  The flag store
+// therefore needs no fence of its own (a release store here costs a MEMBAR.SYS, ~5 us while the fine solve is streaming).
+__global__ void signal_peers_kernel(PeerArgs pa)
+{
+	const unsigned next = *reinterpret_cast<volatile unsigned*>(pa.epoch) + 1u;
+	if ((int)threadIdx.x < pa.world)
+		asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pa.flags[threadIdx.x] + pa.rank), "r"(next) : "memory");
+	__syncwarp();
+	if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(pa.epoch) = next;
+}
+
+// wait until every rank has published apply number *epoch, then pull the foreign level-1 slices into coarseR
+constexpr int kGatherPerThread = 4;
+__global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int first, int count, float4* __restrict__ coarseR)
+{
+	__shared__ int ok;
+	const unsigned want = *reinterpret_cast<volatile unsigned*>(pa.epoch);
+	if (threadIdx.x == 0) ok = 1;
+	__syncthreads();
+	if ((int)threadIdx.x < pa.world)
+	{
+		const unsigned* f = pa.flags[pa.rank] + threadIdx.x;
+		const long long t0 = clock64();
+		// counters only grow; a peer that is already one apply ahead satisfies this too (its data sits in the other buffer)
+		while ((int)(ld_acquire_sys(f) - want) < 0)
+		{
+			if (clock64() - t0 > 4000000000ll) { ok = 0; atomicExch(pa.error, 1u); break; }   // ~2 s: a rank is gone
+			__nanosleep(32);
+		}
+	}
+	__syncthreads();
+	if (!ok) return;
+	const unsigned long long off = (unsigned long long)(want & 1u) * pa.cap;
+	const int stride = gridDim.x * blockDim.x;
+	for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < count; base += kGatherPerThread * stride)
+	{
+		// all remote loads of a thread are issued before the first one is consumed: one NVLink round trip, not one per element
+		const float4* src[kGatherPerThread];
+		float4 v[kGatherPerThread];
+#pragma unroll
+		for (int k = 0; k < kGatherPerThread; ++k)
+		{
+			const int i = first + base + k * stride;
+			src[k] = nullptr;
+			if (base + k * stride < count)
+			{
+				int q = 0;
+				while (q + 1 < pa.world && i >= pa.sliceBegin[q + 1]) ++q;
+				if (q != pa.rank) src[k] = pa.send[q] + off + i;
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < kGatherPerThread; ++k)
+			if (src[k]) v[k] = __ldcg(src[k]);   // written by another GPU: read at the owner's L2, never from this SM's L1
+#pragma unroll
+		for (int k = 0; k < kGatherPerThread; ++k)
+			if (src[k]) coarseR[first + base + k * stride] = v[k];
+	}
 }
 
 // One 32-node group of coarse nodes [begin + 32*bank, ...): sum R over the nodes that share a parent and store it
@@ -385,19 +491,48 @@ static int prolonged_top(const Context* c)
 	return c->optProlongAll ? c->numLevel : (c->numLevel < 4 ? c->numLevel : 4);
 }
 
+static PeerArgs peer_args(const Context* c)
+{
+	PeerArgs pa;
+	for (int q = 0; q < kMaxWorld; ++q) { pa.send[q] = nullptr; pa.flags[q] = nullptr; }
+	for (int q = 0; q <= kMaxWorld; ++q) pa.sliceBegin[q] = 0;
+	for (int q = 0; q < c->world; ++q)
+	{
+		unsigned char* base = (unsigned char*)c->peerArena[q];
+		pa.send[q] = reinterpret_cast<float4*>(base);
+		pa.flags[q] = reinterpret_cast<unsigned*>(base + 2 * sizeof(float4) * c->arenaCap);
+	}
+	for (int q = 0; q <= c->world; ++q) pa.sliceBegin[q] = c->levelSize[1][1] - c->nVC + c->l1Slice[q];
+	unsigned* ctl = reinterpret_cast<unsigned*>((unsigned char*)c->peerArena[c->rank] + 2 * sizeof(float4) * c->arenaCap);
+	pa.epoch = ctl + kMaxWorld;
+	pa.error = ctl + kMaxWorld + 2;
+	pa.cap = c->arenaCap;
+	pa.world = c->world;
+	pa.rank = c->rank;
+	return pa;
+}
+
 int apply_begin(Context* c, const float4* r)
 {
 	cudaStream_t st = c->stream;
 	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
 	if (c->numLevel < 2) return MAS_OK;
-	if (c->world > 1)
+	if (c->world > 1 && !c->p2p)
 	{
 		MAS_CUDA(c, cudaMemsetAsync(c->coarseR.p, 0, sizeof(float4) * (size_t)c->nCoarseNodes, st));
 	}
+	PeerArgs pa;
+	if (c->p2p) pa = peer_args(c);
 	if (ownBanks > 0)
 	{
 		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
-			c->ownFineBegin, c->ownFineEnd, c->coarseR.p);
+			c->ownFineBegin, c->ownFineEnd, c->coarseR.p, c->p2p ? pa.send[c->rank] : nullptr, c->p2p ? pa.cap : 0ull,
+			c->p2p ? pa.epoch : nullptr);
+		c->applyLaunches += 1;
+	}
+	if (c->p2p)
+	{
+		signal_peers_kernel<<<1, 32, 0, st>>>(pa);
 		c->applyLaunches += 1;
 	}
 	return MAS_OK;
@@ -409,6 +544,14 @@ static int launch_coarse(Context* c, cudaStream_t st)
 	if (c->numLevel < 2) return MAS_OK;
 	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
 	const int nCoarseBlocks = c->nCoarseNodes / 32;
+	if (c->p2p)
+	{
+		int grid = cdiv(cnt1, 256 * kGatherPerThread);
+		if (grid > 128) grid = 128;
+		if (grid < 1) grid = 1;
+		gather_peers_kernel<<<grid, 256, 0, st>>>(peer_args(c), begin1 - c->nVC, cnt1, c->coarseR.p);
+		c->applyLaunches += 1;
+	}
 	if (c->numLevel > 2)
 	{
 		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, c->coarseR.p);
@@ -453,17 +596,27 @@ int apply_end(Context* c, const float4* r, float4* z)
 	return MAS_OK;
 }
 
-// Whole apply as a two-branch capture (single-GPU graph path).  `st` is the capturing origin stream; side streams and
+// Whole apply as a two-branch capture (graph path; single GPU, or sharded with the peer-memory exchange).  `st` is the capturing origin stream; side streams and
 // events belong to the context.  headBanks fine banks are solved concurrently with the coarse chain.
 int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 {
 	const int top = prolonged_top(c);
 	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
 	int head = 0;
-	if (top >= 2 && c->optApplyVariant > 0)
+	if (top >= 2 && c->optApplyVariant != 0)
 	{
-		head = (int)((long long)ownBanks * c->optApplyVariant / 1000);
-		head = head / kWarpsPerCta * kWarpsPerCta;
+		if (c->optApplyVariant > 0)
+			head = (int)((long long)ownBanks * c->optApplyVariant / 1000);
+		else
+		{
+			// auto: as many banks as stream in the time the coarse chain takes.  The chain costs a fixed latency (five
+			// dependent launches, the peer wait), the level-0 restriction of the owned vertices and the coarse solves of the
+			// WHOLE mesh; ~330 banks stream per microsecond.  Fitted on the 1M-vertex sweep (optimum 6,500 banks).
+			const long long ownVerts = 32ll * ownBanks;
+			head = (int)(2400 + 5 * ownVerts / 2000 + 3 * (long long)c->nv / 2000);
+			if (c->p2p) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
+		}
+		head = (head + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
 		if (head > ownBanks) head = ownBanks;
 	}
 	if (head == 0)

@@ -398,6 +398,21 @@ int build_hierarchy(Context* c)
 	if (int rc = number_level(c, c->fineMask.p, nv, 0, 0, c->cst[0].p, &n1)) return rc;
 	c->levelSize[1][0] = n1;
 	c->levelSize[1][1] = nVC;
+	// level-1 ids are handed out in Morton order of the fine banks, so the level-1 nodes produced by rank q's banks are the
+	// contiguous range [bankPrefix[firstBank(q)], bankPrefix[firstBank(q+1)]) — the slice its peers pull from it
+	for (int q = 0; q <= 16; ++q) c->l1Slice[q] = n1;
+	c->l1Slice[0] = 0;
+	if (c->world > 1)
+	{
+		const int nBanks = (nv + 31) / 32, nFine = nVC / 32;
+		for (int q = 1; q < c->world; ++q)
+		{
+			const int firstBank = (int)((long long)nFine * q / c->world);
+			if (firstBank < nBanks)
+				MAS_CUDA(c, cudaMemcpyAsync(&c->l1Slice[q], c->bankPrefix.p + firstBank, sizeof(int), cudaMemcpyDeviceToHost, s));
+		}
+		MAS_CUDA(c, cudaStreamSynchronize(s));
+	}
 
 	// ---- level l -> l+1
 	for (int level = 1; level < L; ++level)

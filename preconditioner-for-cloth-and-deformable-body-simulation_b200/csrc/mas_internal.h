@@ -91,7 +91,7 @@ struct Context
 	cudaStream_t stream = nullptr;
 	std::string err;
 	int optProlongAll = 0;
-	int optApplyVariant = 200;   // per-mille of the fine banks solved concurrently with the coarse chain (graph path)
+	int optApplyVariant = -1;    // fine banks solved concurrently with the coarse chain: -1 auto, 0 none, >0 per-mille of the owned banks
 	int optUseGraph = 1;
 	int optTimeKernels = 0;
 	int rank = 0, world = 1;
@@ -158,8 +158,16 @@ struct Context
 	int pcgLaunchesPerIter = 0;
 	int pcgConverged = 0;
 
+	// peer-memory exchange (world > 1): arena = [send0][send1][flags kMaxWorld][epoch][-][error]
+	DevBuf<unsigned char> arena;
+	size_t arenaCap = 0;              // float4 elements per receive buffer
+	void* peerArena[16] = {};         // arena base of every rank, peer-mapped; [rank] is the local one
+	bool peerOpened[16] = {};         // opened through cudaIpcOpenMemHandle (must be closed)
+	bool p2p = false;
+
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
+	int l1Slice[17] = {};              // level-1 nodes (level-local ids) produced by rank q: [l1Slice[q], l1Slice[q+1])
 
 	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
 	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)

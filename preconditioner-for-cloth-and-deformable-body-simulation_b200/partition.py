@@ -8,7 +8,12 @@ The reference is single-process (OpenMP only); this layer is new.  What shards a
     r -> R_1 is local; every rank then needs the complete coarse residual, which is ONE sum over ranks of the small
     coarse buffer per apply (0.54 MB at 1M vertices): `exchange(1)`;
   * setup has ONE sum over ranks of the coarse Galerkin accumulators (FP64): `exchange(0)`;
-  * levels >= 1 are solved redundantly on every rank (3 % of the blocks), which removes any exchange of z.
+  * levels >= 1 are solved redundantly on every rank (3 % of the blocks), which removes any exchange of z;
+  * production path for the apply exchange: `attach_peers()` maps every rank's exchange arena into every other rank
+    (CUDA IPC handles travel over torch.distributed once); from then on the level-0 restriction kernel itself stores
+    the level-1 residuals into all peers over NVLink and raises a flag, the coarse levels wait on the flags on the
+    device, and Preconditioning() is a single graph launch per rank — no NCCL call and no host sync per apply.
+    Without attached peers the exchange is one `all_reduce` between apply_begin and apply_end (the baseline).
 
 `ShardedSchwarzPreconditioner` drives a per-rank engine through begin -> exchange -> end.  The engine is
 `SeSchwarzPreconditioner` (CUDA, exchange buffers are device tensors, NCCL) in production; the CPU tests inject a
@@ -47,6 +52,29 @@ class ShardedSchwarzPreconditioner:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._apply_exchange = None
+        self.p2p = False
+
+    def attach_peers(self) -> bool:
+        """Exchange the IPC handles of the per-rank arenas and attach them (call after AllocatePrecoditioner).
+        Returns False (and stays on the all-reduce path) if peer mapping is not available on this machine."""
+        if self.world < 2:
+            return False
+        handles = [None] * self.world
+        try:
+            mine = self.engine.peer_export()
+        except Exception:
+            mine = None
+        self.dist.all_gather_object(handles, mine, group=self.group)
+        ok = all(h is not None for h in handles)
+        if ok:
+            try:
+                self.engine.peer_attach(handles=handles)
+            except Exception:
+                ok = False
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok, group=self.group)
+        self.p2p = all(flags)
+        return self.p2p
 
     def _sum_over_ranks(self, tensor):
         if self.world > 1 and tensor.numel():
@@ -65,6 +93,8 @@ class ShardedSchwarzPreconditioner:
 
     def Preconditioning(self, z, residual, dim: int = 0):  # noqa: N802
         """z[own vertices] = M^-1 residual; entries of other ranks' vertices are left untouched."""
+        if self.p2p:
+            return self.engine.Preconditioning(z, residual, dim)
         self.engine.apply_begin(residual)
         self._sum_over_ranks(self._apply_exchange)
         self.engine.apply_end(z)

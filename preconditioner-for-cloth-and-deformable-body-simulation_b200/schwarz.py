@@ -23,7 +23,7 @@ MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
 OPT_PROLONG_ALL_LEVELS, OPT_APPLY_VARIANT, OPT_USE_GRAPH, OPT_TIME_KERNELS = 0, 1, 2, 3
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
  INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
- INT_PCG_CONVERGED) = range(13)
+ INT_PCG_CONVERGED, INT_PEER_ERROR) = range(14)
 (ARR_MORTON, ARR_SORTED_GET_ORIGINAL, ARR_ORIGINAL_GET_SORTED, ARR_GOING_NEXT, ARR_LEVEL_SIZE, ARR_FINE_CONNECT_MASK,
  ARR_COARSE_SPACE_TABLE, ARR_COARSE_TABLES, ARR_SORTED_ADJ_STARTS, ARR_SORTED_ADJ_IDX, ARR_STENCILS,
  ARR_STENCIL_INDEX_MAPPED, ARR_DENSE_INVERSE, ARR_MAPPED_R, ARR_MAPPED_Z, ARR_AABB) = range(16)
@@ -33,7 +33,7 @@ EXPORTS = [
     "mas_create", "mas_destroy", "mas_last_error", "mas_set_stream", "mas_set_option", "mas_set_partition",
     "mas_allocate", "mas_prepare", "mas_apply", "mas_prepare_begin", "mas_prepare_end", "mas_apply_begin",
     "mas_apply_end", "mas_exchange_buffer", "mas_get_int", "mas_get_array", "mas_morton_encode", "mas_get_timing",
-    "mas_pcg_solve",
+    "mas_pcg_solve", "mas_peer_export", "mas_peer_local", "mas_peer_attach",
 ]
 
 _lib = None
@@ -72,6 +72,9 @@ def load_library() -> C.CDLL:
     lib.mas_get_array.argtypes = [vp, i, i, vp, C.c_size_t]
     lib.mas_morton_encode.argtypes = [vp, vp, i, vp]
     lib.mas_get_timing.argtypes = [vp, i, C.POINTER(C.c_float)]
+    lib.mas_peer_export.argtypes = [vp, vp]
+    lib.mas_peer_local.argtypes = [vp, C.POINTER(vp)]
+    lib.mas_peer_attach.argtypes = [vp, vp, C.POINTER(vp)]
     lib.mas_pcg_solve.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_float, i, i, i, C.POINTER(i), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "mas_last_error":
@@ -220,6 +223,31 @@ class SeSchwarzPreconditioner:
         t = torch.as_tensor(w, device=f"cuda:{self.device}")
         assert t.dtype == dtype and t.data_ptr() == ptr
         return t
+
+    # ---- peer-memory exchange (multi-GPU, NVLink)
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange arena (send it to the other processes)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.mas_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_local(self) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.mas_peer_local(self.h, C.byref(p)))
+        return int(p.value)
+
+    def peer_attach(self, handles=None, pointers=None):
+        """handles: list of `world` 64-byte handles in rank order; pointers: list of `world` device pointers (0/None = use
+        the handle).  After this, Preconditioning() on a sharded context is a single call again."""
+        hb = b"".join(handles) if handles is not None else None
+        hp = C.c_char_p(hb) if hb is not None else None
+        pp = None
+        if pointers is not None:
+            pp = (C.c_void_p * len(pointers))(*[C.c_void_p(int(p) if p else 0) for p in pointers])
+        self._ck(self.lib.mas_peer_attach(self.h, hp, pp))
+
+    @property
+    def peer_error(self): return self.get_int(INT_PEER_ERROR)
 
     # ---- introspection (parity tests)
     def get_int(self, key: int) -> int:

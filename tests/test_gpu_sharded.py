@@ -84,6 +84,71 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
     assert rel_l2(merged.cpu().numpy(), z1.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth256", 4)])
+def test_peer_memory_exchange_in_one_process(name, world, pkg, synth):
+    """The production exchange (restriction kernel stores into every rank's arena + device-side flags) with all shards
+    living in this process on one GPU, each on its own stream so that they really run concurrently and wait for each
+    other on the device.  Results must equal the all-reduce protocol bit for bit, and repeat exactly."""
+    import torch
+    mesh = _mesh(synth, name)
+    r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    shards = [pkg.SeSchwarzPreconditioner(0, rank=k, world=world, stream=streams[k]) for k in range(world)]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    raw = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), np.uint8).copy()).cuda()
+    d = dict(pos=dev(mesh.positions), edges=dev(mesh.edges) if mesh.ne else None, faces=dev(mesh.faces) if mesh.nf else None,
+             st=dev(mesh.nbr_starts), ix=dev(mesh.nbr_idx), diag=dev(mesh.diag), off=dev(mesh.offdiag),
+             ef=raw(mesh.ef) if mesh.ef.size else None, ee=raw(mesh.ee) if mesh.ee.size else None, vf=raw(mesh.vf) if mesh.vf.size else None)
+    torch.cuda.synchronize()
+    for g in shards:
+        g.m_positions, g.m_edges, g.m_faces, g.m_neighbours = d["pos"], d["edges"], d["faces"], (d["st"], d["ix"])
+        g.AllocatePrecoditioner(mesh.nv, mesh.ne, mesh.nf)
+    arenas = [g.peer_local() for g in shards]
+    for g in shards:
+        g.PreparePreconditioner(d["diag"], d["off"], d["st"], d["ef"], d["ee"], d["vf"], mesh.ef_total, mesh.ee_total, mesh.vf_total,
+                                phase="begin")
+    torch.cuda.synchronize()
+    total = sum(g.exchange_tensor(0).clone() for g in shards)
+    for g in shards:
+        g.exchange_tensor(0).copy_(total)
+    torch.cuda.synchronize()
+    for g in shards:
+        g.prepare_end()
+
+    # reference: the all-reduce protocol on the same shards
+    z_ref = [torch.zeros_like(r) for _ in shards]
+    for g in shards:
+        g.apply_begin(r)
+    torch.cuda.synchronize()
+    total = sum(g.exchange_tensor(1).clone() for g in shards)
+    for g, z in zip(shards, z_ref):
+        g.exchange_tensor(1).copy_(total)
+    torch.cuda.synchronize()
+    for g, z in zip(shards, z_ref):
+        g.apply_end(z)
+    torch.cuda.synchronize()
+
+    for g in shards:
+        g.peer_attach(pointers=arenas)
+    zs = [torch.zeros_like(r) for _ in shards]             # same buffers every time: the apply graph is captured once per shard
+    for rep in range(4):                                   # several applies: the double-buffered arenas and counters roll over
+        for z in zs:
+            z.zero_()
+        torch.cuda.synchronize()
+        for g, z in zip(shards, zs):
+            g.Preconditioning(z, r)                        # enqueue only; the shards meet on the device
+        torch.cuda.synchronize()
+        for g, z, zr in zip(shards, zs, z_ref):
+            assert g.peer_error == 0
+            assert torch.equal(z, zr), rep
+    merged = sum(zs)
+    single = pkg.SeSchwarzPreconditioner(0).setup_from_mesh(mesh, device_inputs=True)
+    z1 = torch.empty_like(r)
+    single.Preconditioning(z1, r)
+    torch.cuda.synchronize()
+    assert rel_l2(merged.cpu().numpy(), z1.cpu().numpy()) < 1e-5
+
+
 def _nccl_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -104,6 +169,18 @@ def _nccl_worker(rank, world, port, q):
         r = dev(pkg.synth.residual(mesh.nv))
         z = torch.zeros_like(r)
         drv.Preconditioning(z, r)
+        torch.cuda.synchronize()
+        z_allreduce = z.clone()
+        # the same apply through the peer-memory exchange (IPC-mapped arenas): bit-identical shard results
+        p2p = drv.attach_peers()
+        same = True
+        if p2p:
+            z2 = torch.zeros_like(r)
+            for _ in range(4):
+                z2.zero_()
+                drv.Preconditioning(z2, r)
+                torch.cuda.synchronize()
+                same = same and bool(torch.equal(z2, z_allreduce)) and eng.peer_error == 0
         dist.all_reduce(z)                                        # disjoint shards, zeros elsewhere -> the full z
         torch.cuda.synchronize()
         if rank == 0:
@@ -111,7 +188,9 @@ def _nccl_worker(rank, world, port, q):
             z1 = torch.empty_like(r)
             one.Preconditioning(z1, r)
             torch.cuda.synchronize()
-            q.put(float((z - z1)[:, :3].norm() / z1[:, :3].norm()))
+            q.put((float((z - z1)[:, :3].norm() / z1[:, :3].norm()), p2p, same))
+        else:
+            q.put((0.0, p2p, same))
     finally:
         dist.destroy_process_group()
 
@@ -133,4 +212,7 @@ def test_two_gpus_over_nccl_match_single_device():
     for p in procs:
         p.join(timeout=300)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert q.get(timeout=5) < 1e-5
+    res = [q.get(timeout=5) for _ in range(2)]
+    assert max(e for e, _, _ in res) < 1e-5
+    assert all(p2p for _, p2p, _ in res), "CUDA IPC peer mapping unavailable on this box"
+    assert all(same for _, _, same in res)
