@@ -195,6 +195,50 @@ def test_symmetry_linearity_and_definiteness_full_size(gpu_cls, synth):
     assert torch.equal(z1b, z1)
 
 
+@pytest.mark.parametrize("cfg", [3, 4])
+def test_full_size_tet_cube_and_five_level_cloth(cfg, gpu_cls, synth):
+    """BASELINE configs 3 (tet cube, 1,048,576 verts, up to 14 neighbours) and 4 (2048^2 cloth, 4,194,304 verts, FIVE
+    levels) at full size: hierarchy sizes, and the size-independent properties of M^-1 (linear, symmetric, positive
+    definite, deterministic, w = 0).  Config 4's level sizes are the correct-scan values 131072/4096/128/4 (the
+    reference's truncated scan, Q5, yields 131072/1056/33/2), and with five levels the top one
+    is solved but not prolonged unless MAS_OPT_PROLONG_ALL_LEVELS is set (Q4)."""
+    import torch
+    mesh = synth.config(cfg)
+    g = gpu_cls(0).setup_from_mesh(mesh, device_inputs=True)
+    ls = g.level_size().tolist()
+    if cfg == 4:
+        assert g.num_level == 5
+        assert ls == [[0, 0], [131072, 4194304], [4096, 4325376], [128, 4329472], [4, 4329600], [1, 4329632]]
+        assert synth.fnv1a_i32(g.sorted_get_original()) == 0xa68a9dc5          # SURVEY 8c known answers
+        assert synth.fnv1a_i32(g.going_next()[:mesh.nv]) == 0xc6489dc5
+    else:
+        assert g.num_level == 4 and ls[1][0] == 32768 and ls[2][0] == 1024 and ls[3][0] == 32 and ls[4][0] == 1
+    r1 = torch.from_numpy(synth.residual(mesh.nv, 1)).cuda()
+    r2 = torch.from_numpy(synth.residual(mesh.nv, 2)).cuda()
+    z1, z2, z12 = torch.empty_like(r1), torch.empty_like(r1), torch.empty_like(r1)
+    g.Preconditioning(z1, r1)
+    g.Preconditioning(z2, r2)
+    g.Preconditioning(z12, 2.0 * r1 - 0.5 * r2)
+    torch.cuda.synchronize()
+    d = lambda a, b: float((a[:, :3].double() * b[:, :3].double()).sum())
+    assert abs(d(r1, z2) - d(r2, z1)) <= 1e-4 * abs(d(r1, z1))
+    assert d(r1, z1) > 0 and d(r2, z2) > 0
+    lin = 2.0 * z1 - 0.5 * z2
+    assert float((z12 - lin)[:, :3].norm() / lin[:, :3].norm()) < 1e-5
+    assert bool((z1[:, 3] == 0).all())
+    z1b = torch.empty_like(r1)
+    g.Preconditioning(z1b, r1)
+    torch.cuda.synchronize()
+    assert torch.equal(z1b, z1)
+    if cfg == 4:
+        g.set_option(0, 1)                                       # prolong the fifth level too
+        z1c = torch.empty_like(r1)
+        g.Preconditioning(z1c, r1)
+        torch.cuda.synchronize()
+        diff = float((z1c - z1)[:, :3].norm() / z1[:, :3].norm())
+        assert 0 < diff < 0.5
+
+
 def test_config1_512_with_collisions_vs_oracle(gpu_cls, synth, oracle_lib):
     """BASELINE config 1: 512x512 cloth (262k verts) with synthetic EF/EE/VF stencils, 1-GPU setup + apply."""
     mesh = synth.config(1)
