@@ -6,7 +6,10 @@
 One "step" = one Preconditioning() apply (the per-PCG-iteration hot path, SeSchwarzPreconditioner.cpp:100-110) over
 the whole synthetic mesh.  N>1 is launched by torchrun (one rank per GPU); the 32-node fine domains are sharded in
 Morton-contiguous ranges and the only data-path exchange is one NCCL all-reduce of the coarse-level residuals per
-apply (and one of the coarse Galerkin accumulators per setup).  Total work is fixed as N grows ("strong").
+apply (and one of the coarse Galerkin accumulators per setup).  Scaling (N>1, default config): "weak" (default) shards ONE
+cloth of N x 1,048,576 vertices (1024x1024, 2048x1024, 2048x2048, 4096x2048 for N = 1, 2, 4, 8), i.e. per-GPU work is
+fixed at the 1M-vertex cloth the metric is quoted on and `value` counts 1M-vertex applies/s over all ranks
+(N x whole-mesh applies/s); "--scaling strong" keeps the 1M-vertex mesh and splits it N ways (latency-bound from N = 4).
 
 Keys beyond the base contract:
   value          applies/s with r and z resident in HBM (CUDA events on the launching stream, max over ranks)
@@ -180,8 +183,10 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "applies/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / mean_rate, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "nv": mesh.nv, "timing": "host wall clock, mean over steps"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "nv": mesh.nv, "timing": "host wall clock, mean over steps",
+                   "units": "1M-vertex applies/s; with --gpus N (weak scaling) the GPU arm shards N such units, the CPU arm times one "
+                            "unit on all host threads (its throughput per unit does not depend on the mesh size)"},
         "setup_ms": setup_ms,
         "cpu_baseline": {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
                          "sample": f"whole mesh, {steps} applies after 1 setup + warm-up; best single apply {1e3 / best_rate:.2f} ms"},
@@ -210,13 +215,27 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     pkg = importlib.import_module(PKG_NAME)
     S = pkg.synth
-    mesh = S.config(args.config)
-    nv = mesh.nv
     dev = f"cuda:{local}"
+    weak = world > 1 and args.scaling == "weak" and args.config == 2
+    workload = WORKLOADS[args.config]
+    if args.config == 2:
+        # generated on the device (bit-identical to the numpy recipe, tests/test_synth.py): no multi-GB host pass per rank
+        b = 1
+        while weak and (b * 2) * (b * 2) <= world and world % (b * 2) == 0:
+            b *= 2
+        a = world // b if weak else 1
+        mesh = S.cloth_rect_device(1024 * a, 1024 * b, torch.device(dev))
+        if weak:
+            workload = (f"cloth {1024 * a}x{1024 * b} ({mesh.nv:,} verts = {world} x 1,048,576), 8-neighbour springs, "
+                        f"Morton-sharded over {world} GPUs")
+    else:
+        mesh = S.config(args.config)
+    nv = mesh.nv
+    units = nv / 1048576.0 if weak else 1.0      # 1M-vertex applies per whole-mesh apply
 
     stream = torch.cuda.current_stream()
     g = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=stream)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     tb = lambda a: torch.from_numpy(np.frombuffer(np.ascontiguousarray(a).tobytes(), np.uint8).copy()).to(dev)
     g.m_positions = t(mesh.positions)
     g.m_edges = t(mesh.edges) if mesh.ne else None
@@ -352,6 +371,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    if torch.is_tensor(mesh.positions) and world == 1:
+        # host copy for the CPU reference leg
+        for name in ("positions", "nbr_starts", "nbr_idx", "diag", "offdiag"):
+            setattr(mesh, name, getattr(mesh, name).cpu().numpy())
     n_blocks = g.num_blocks
     lv = g.level_size().tolist()
     n_fine = ((nv + 31) // 32)
@@ -397,19 +420,35 @@ def run_ours(args):
         if args.cpu_pcg:
             cpu["pcg"] = cpu_reference_pcg(mesh, S.residual(nv), threads)
 
+    if world > 1:
+        # per-rank share of the algorithmic bytes against one GPU's HBM peak (whole apply; no kernel-only timing here)
+        b0, b1 = g.owned_fine_blocks
+        own_verts = max(0, min(32 * b1, nv) - min(32 * b0, nv))
+        own_blocks = (b1 - b0) + (n_blocks - n_fine) / world
+        rank_bytes = own_blocks * 4656 * 4 + 32 * own_verts
+        roof = {"bound": "hbm", "kernel": "whole sharded apply, rank 0 share (level-0 solve dominates)",
+                "achieved": rank_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": rank_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(rank_bytes), "traffic": None}
     out = {
-        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak" if (weak or world == 1 and args.scaling == "weak") else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "nv": nv, "levels": lv, "blocks": n_blocks,
-                   "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step vs 126 MB L2",
+        "config": {"workload": workload, "nv": nv, "levels": lv, "blocks": n_blocks,
+                   "units": (f"value = {units:g} x whole-mesh applies/s: one apply of the sharded {nv:,}-vertex mesh counts as "
+                             f"{units:g} applies of the 1M-vertex cloth (per-GPU work fixed)") if weak else "whole-mesh applies/s",
+                   "mesh_applies_per_s": 1e3 / ms_per_step,
+                   "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step per GPU vs 126 MB L2",
                    "timing": "CUDA events on the launching stream, max over ranks",
                    "parallelism": (f"morton-sharded x{world}, " + ("peer-memory exchange fused into the restriction kernel (NVLink)"
                                                                       if p2p else "NCCL all-reduce of coarse residuals"))
                    if world > 1 else "single GPU"},
         "setup_ms": setup_ms, "setup_device_ms": setup_device_ms,
-        "e2e": {"value": e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv, "d2h_bytes_per_step": 16 * nv,
-                "steps": e2e_steps},
+        "e2e": {"value": units * e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv * world,
+                "d2h_bytes_per_step": 16 * nv * world, "steps": e2e_steps,
+                "note": "every rank copies the whole r in and its z out over its own PCIe link" if world > 1 else
+                        "mas_apply(MAS_MEM_HOST): pinned host r -> H2D -> apply graph -> D2H z, synchronous"},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "pcg": pcg,
     }
@@ -425,6 +464,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, help="index into BASELINE.json configs (default 2: 1M-vertex cloth)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1 with the default config: weak = one N x 1M-vertex cloth (default), strong = the 1M-vertex cloth split N ways")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
     ap.add_argument("--variant", type=int, default=None, help="MAS_OPT_APPLY_VARIANT override (development sweeps)")

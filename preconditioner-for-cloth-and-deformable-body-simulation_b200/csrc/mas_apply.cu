@@ -397,12 +397,14 @@ __device__ __forceinline__ Vec3 solve_quarter(const float* __restrict__ blk, int
 // SchwarzLocalXSym on the blocks of levels >= 1 (cpp:1600-1696).  There are few of them (3 % of all blocks), so the kernel
 // is latency-bound: FOUR warps share a block, each streaming one quarter of it in a single batch of loads, and the four
 // partial products are added in a fixed order.
+// The grid covers the coarse blocks this rank solves: `ownL1` level-1 blocks starting at l1Begin, then all blocks from
+// topBegin on (levels >= 2); a single-GPU context owns every level-1 block.
 __global__ void __launch_bounds__(128) solve_coarse_kernel(const float* __restrict__ packed, const float4* __restrict__ coarseR,
-	float4* __restrict__ coarseZ)
+	float4* __restrict__ coarseZ, int l1Begin, int ownL1, int topBegin)
 {
 	__shared__ float part[3][32][3];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int blk = blockIdx.x;
+	const int blk = (int)blockIdx.x < ownL1 ? l1Begin + blockIdx.x : topBegin + (blockIdx.x - ownL1);
 	const float4 rv = coarseR[blk * 32 + lane];
 	const Vec3 x = { rv.x, rv.y, rv.z };
 	const float* base = packed + (size_t)blk * kTri;
@@ -422,11 +424,11 @@ __global__ void __launch_bounds__(128) solve_coarse_kernel(const float* __restri
 }
 
 // what CollectFinalZ (cpp:1698-1719) adds to every vertex below a level-1 node: Z_1 + Z_2[parent] + ...
-__global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int* __restrict__ goingNext, int begin1, int count1,
-	int nVC, int extraLevels, float4* __restrict__ zsum)
+__global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int* __restrict__ goingNext, int begin1, int first,
+	int last, int nVC, int extraLevels, float4* __restrict__ zsum)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count1) return;
+	const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= last) return;
 	int node = begin1 + i;
 	float4 z = coarseZ[node - nVC];
 	for (int l = 0; l < extraLevels; ++l)
@@ -566,11 +568,23 @@ static int launch_coarse(Context* c, cudaStream_t st)
 		restrict_top_kernel<<<1, kTopThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p);
 		c->applyLaunches += 1;
 	}
-	solve_coarse_kernel<<<nCoarseBlocks, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
-		c->coarseZ.p);
-	c->applyLaunches += 1;
-	prolong_sum_kernel<<<cdiv(cnt1, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, begin1, cnt1, c->nVC, prolonged_top(c) - 2, c->coarseZsum.p);
-	c->applyLaunches += 1;
+	// level-1 blocks stay partitioned (each rank solves the blocks that hold its own level-1 nodes); levels >= 2 are solved
+	// redundantly on every rank, which removes any exchange of z
+	const int ownL1 = c->l1BlockEnd - c->l1BlockBegin;
+	const int solved = ownL1 + (nCoarseBlocks - c->nL1Blocks);
+	if (solved > 0)
+	{
+		solve_coarse_kernel<<<solved, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
+			c->coarseZ.p, c->l1BlockBegin, ownL1, c->nL1Blocks);
+		c->applyLaunches += 1;
+	}
+	const int first = c->world > 1 ? c->l1Slice[c->rank] : 0, last = c->world > 1 ? c->l1Slice[c->rank + 1] : cnt1;
+	if (last > first)
+	{
+		prolong_sum_kernel<<<cdiv(last - first, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, begin1, first, last, c->nVC,
+			prolonged_top(c) - 2, c->coarseZsum.p);
+		c->applyLaunches += 1;
+	}
 	return MAS_OK;
 }
 
@@ -610,10 +624,11 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		else
 		{
 			// auto: as many banks as stream in the time the coarse chain takes.  The chain costs a fixed latency (five
-			// dependent launches, the peer wait), the level-0 restriction of the owned vertices and the coarse solves of the
-			// WHOLE mesh; ~330 banks stream per microsecond.  Fitted on the 1M-vertex sweep (optimum 6,500 banks).
+			// dependent launches, the peer wait), the level-0 restriction of the owned vertices and the coarse solves above them
+			// (level 1 is partitioned like the fine banks); ~330 banks stream per microsecond.  Fitted on the 1M-vertex sweep
+			// (optimum 6,500 banks).
 			const long long ownVerts = 32ll * ownBanks;
-			head = (int)(2400 + 5 * ownVerts / 2000 + 3 * (long long)c->nv / 2000);
+			head = (int)(2400 + 8 * ownVerts / 2000);
 			if (c->p2p) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
 		}
 		head = (head + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;

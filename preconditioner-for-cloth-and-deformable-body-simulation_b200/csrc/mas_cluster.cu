@@ -413,6 +413,15 @@ int build_hierarchy(Context* c)
 		}
 		MAS_CUDA(c, cudaStreamSynchronize(s));
 	}
+	c->nL1Blocks = pad32(n1) / 32;
+	c->l1BlockBegin = 0;
+	c->l1BlockEnd = c->nL1Blocks;
+	if (c->world > 1)
+	{
+		const int a = c->l1Slice[c->rank], b = c->l1Slice[c->rank + 1];
+		c->l1BlockBegin = a / 32;
+		c->l1BlockEnd = b > a ? (b + 31) / 32 : c->l1BlockBegin;
+	}
 
 	// ---- level l -> l+1
 	for (int level = 1; level < L; ++level)

@@ -168,6 +168,9 @@ struct Context
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
 	int l1Slice[17] = {};              // level-1 nodes (level-local ids) produced by rank q: [l1Slice[q], l1Slice[q+1])
+	// Coarse blocks this rank inverts and solves: the level-1 blocks [l1BlockBegin, l1BlockEnd) that hold its own level-1
+	// nodes (a block straddling two shards is done by both) plus every block of levels >= 2, [nL1Blocks, nCoarseBlocks).
+	int l1BlockBegin = 0, l1BlockEnd = 0, nL1Blocks = 0;
 
 	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
 	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)

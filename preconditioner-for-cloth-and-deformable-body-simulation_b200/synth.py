@@ -119,13 +119,21 @@ def _spring_hessian(positions, starts, idx, src, k, m, skew=0.0):
 def cloth(n: int, k: float = 1000.0, m: float = 1.0, with_topology: bool = False,
           skew: float = 0.0, spacing: float = 0.01) -> Mesh:
     """Planar N x N cloth, 8-neighbour springs (BASELINE.md §3 recipe)."""
-    nv = n * n
+    return cloth_rect(n, n, k, m, with_topology, skew, spacing)
+
+
+def cloth_rect(nx: int, ny: int, k: float = 1000.0, m: float = 1.0, with_topology: bool = False,
+               skew: float = 0.0, spacing: float = 0.01) -> Mesh:
+    """Planar nx x ny cloth (v = j*nx + i), same springs and insertion order as the square recipe.  Power-of-two sides
+    keep the Morton banks 8x4 patches (the per-axis normalisation of cpp:225 stretches the shorter side)."""
+    n = nx
+    nv = nx * ny
     v = np.arange(nv, dtype=np.int64)
     i, j = v % n, v // n
     positions = np.zeros((nv, 4), np.float32)
     positions[:, 0] = (np.float32(spacing) * i.astype(np.float32))
     positions[:, 1] = (np.float32(spacing) * j.astype(np.float32))
-    right, down = i + 1 < n, j + 1 < n
+    right, down = i + 1 < nx, j + 1 < ny
     # per v, in order: (v,v+1), (v,v+N), (v,v+N+1), (v+1,v+N)
     a = np.stack([v, v, v, v + 1], 1)
     b = np.stack([v + 1, v + n, v + n + 1, v + n], 1)
@@ -133,18 +141,67 @@ def cloth(n: int, k: float = 1000.0, m: float = 1.0, with_topology: bool = False
     a, b = a[ok], b[ok]                               # row-major boolean mask keeps scan order
     starts, idx, src = _csr_from_edge_sequence(nv, a, b)
     diag, off = _spring_hessian(positions, starts, idx, src, k, m, skew)
-    mesh = Mesh(f"cloth{n}x{n}", nv, positions, starts, idx, diag, off)
+    mesh = Mesh(f"cloth{nx}x{ny}", nv, positions, starts, idx, diag, off)
     if with_topology:
-        mesh.edges, mesh.faces = _cloth_topology(n)
+        mesh.edges, mesh.faces = _cloth_topology(nx, ny)
     return mesh
 
 
-def _cloth_topology(n: int):
+def cloth_rect_device(nx: int, ny: int, device, k: float = 1000.0, m: float = 1.0, spacing: float = 0.01):
+    """The same mesh as cloth_rect(nx, ny, k, m), generated with torch ON `device` (bit-identical arrays; checked by
+    tests/test_synth.py): multi-million-vertex meshes for the sharded bench without a 13 GB / 45 s numpy pass per rank.
+    Returns a Mesh whose array fields are torch tensors on `device`.
+
+    adj[u] in insertion order of the square recipe is the fixed candidate list
+    u-N-1, u-N, u-N+1, u-1, u+N-1, u+1, u+N, u+N+1 filtered by the grid bounds."""
+    import torch
+    nv = nx * ny
+    v = torch.arange(nv, dtype=torch.int64, device=device)
+    i, j = v % nx, v // nx
+    positions = torch.zeros((nv, 4), dtype=torch.float32, device=device)
+    positions[:, 0] = torch.tensor(spacing, dtype=torch.float32, device=device) * i.to(torch.float32)
+    positions[:, 1] = torch.tensor(spacing, dtype=torch.float32, device=device) * j.to(torch.float32)
+    left, right, up, down = i >= 1, i + 1 < nx, j >= 1, j + 1 < ny
+    offs = [-nx - 1, -nx, -nx + 1, -1, nx - 1, 1, nx, nx + 1]
+    oks = [left & up, up, up & right, left, left & down, right, down, right & down]
+    valid = torch.stack(oks, 1)                                          # [nv, 8]
+    cand = torch.stack([v + o for o in offs], 1)
+    starts = torch.zeros(nv + 1, dtype=torch.int64, device=device)
+    torch.cumsum(valid.sum(1), 0, out=starts[1:])
+    idx = cand[valid]                                                    # row-major mask keeps the candidate order
+    del cand
+    p = positions[:, :3]
+    kk = torch.tensor(k, dtype=torch.float32, device=device)
+    eye = torch.eye(3, dtype=torch.float32, device=device)
+    kdiag = torch.tensor(0.1 * k, dtype=torch.float32, device=device) * eye
+    diag = torch.zeros((nv, 3, 3), dtype=torch.float32, device=device)
+    off_full = torch.empty((nv, 8, 3, 3), dtype=torch.float32, device=device)
+    for c, (o, ok) in enumerate(zip(offs, oks)):
+        dst = torch.where(ok, v + o, v)
+        d = p[dst] - p
+        ln = torch.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+        ln = torch.where(ok, ln, torch.ones_like(ln))
+        d = d / ln[:, None]
+        K = (kk * d[:, :, None]) * d[:, None, :]
+        K = K + kdiag[None]
+        K = torch.where(ok[:, None, None], K, torch.zeros_like(K))
+        diag = diag + K
+        off_full[:, c] = -K
+    diag = diag + (torch.tensor(m, dtype=torch.float32, device=device) * eye)[None]
+    off = off_full[valid]                                                # [nnz, 3, 3]
+    del off_full
+    off_cm = off.transpose(1, 2).contiguous().reshape(-1, 9)
+    diag_cm = diag.transpose(1, 2).contiguous().reshape(-1, 9)
+    return Mesh(f"cloth{nx}x{ny}", nv, positions, starts.to(torch.int32), idx.to(torch.int32), diag_cm, off_cm)
+
+
+def _cloth_topology(n: int, ny: int = 0):
     """Triangles (v,v+1,v+N),(v+1,v+N+1,v+N) and their unique edges as Int4 rows.
     Only [0],[1] of an edge and [0..2] of a face are read (cpp:338-342)."""
-    v = np.arange(n * n, dtype=np.int64)
+    ny = ny or n
+    v = np.arange(n * ny, dtype=np.int64)
     i, j = v % n, v // n
-    q = v[(i + 1 < n) & (j + 1 < n)]
+    q = v[(i + 1 < n) & (j + 1 < ny)]
     f0 = np.stack([q, q + 1, q + n, np.zeros_like(q)], 1)
     f1 = np.stack([q + 1, q + n + 1, q + n, np.zeros_like(q)], 1)
     faces = np.empty((2 * q.shape[0], 4), np.int64)
@@ -288,3 +345,15 @@ def config(index: int) -> Mesh:
     if index == 4:
         return cloth(2048)
     raise ValueError(index)
+
+
+def weak_scaling_cloth(n_gpus: int) -> Mesh:
+    """One sharded cloth with 1,048,576 vertices PER GPU (bench.py --scaling weak): 1024x1024, 2048x1024, 2048x2048,
+    4096x2048 for 1/2/4/8 GPUs; in general 1024*a x 1024*b with a*b = n_gpus, a >= b, both powers of two when possible."""
+    if n_gpus < 1:
+        raise ValueError(n_gpus)
+    b = 1
+    while (b * 2) * (b * 2) <= n_gpus and n_gpus % (b * 2) == 0:
+        b *= 2
+    a = n_gpus // b
+    return cloth_rect(1024 * a, 1024 * b)

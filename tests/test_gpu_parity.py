@@ -27,11 +27,12 @@ def _cases(synth):
         "cloth128_dense_collisions": lambda: coll(128, frac=1),
         "tet16x16x8": lambda: synth.tet_cube(16, 16, 8),
         "cloth200_stiff": lambda: synth.cloth(200, k=1e5),        # ill-conditioned blocks
+        "cloth_rect96x40": lambda: synth.cloth_rect(96, 40),      # per-axis Morton normalisation on a non-square sheet
     }
 
 
 CASE_NAMES = ["cloth64", "cloth50_ragged", "cloth7_tiny", "cloth5_single_bank", "cloth64_skew", "cloth96_collisions",
-              "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff"]
+              "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff", "cloth_rect96x40"]
 
 
 @pytest.fixture(scope="module")

@@ -28,10 +28,13 @@ def _mesh(synth, name):
         return synth.cloth(50)
     if name == "cloth256":
         return synth.cloth(256)
+    if name == "cloth_rect512x256":
+        return synth.cloth_rect(512, 256)          # 4 levels; level-1 blocks straddle the shard cuts at world = 3, 8
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth50_ragged", 3), ("cloth256", 4)])
+@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth50_ragged", 3), ("cloth256", 4),
+                                        ("cloth_rect512x256", 8), ("cloth_rect512x256", 3)])
 def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
     import torch
     mesh = _mesh(synth, name)
@@ -84,7 +87,7 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
     assert rel_l2(merged.cpu().numpy(), z1.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth256", 4)])
+@pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth256", 4), ("cloth_rect512x256", 8)])
 def test_peer_memory_exchange_in_one_process(name, world, pkg, synth):
     """The production exchange (restriction kernel stores into every rank's arena + device-side flags) with all shards
     living in this process on one GPU, each on its own stream so that they really run concurrently and wait for each
