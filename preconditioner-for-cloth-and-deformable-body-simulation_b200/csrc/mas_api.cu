@@ -1,6 +1,7 @@
 // extern "C" boundary of libmas_b200.so (include/mas_b200.h): argument checking, host<->device staging,
 // CUDA-graph capture of the apply sequence, and read-only introspection for the parity tests.
 #include "mas_internal.h"
+#include <cstdlib>
 
 #include <cstdio>
 #include <cstring>
@@ -338,6 +339,7 @@ static int run_apply_device(Context* c, const float4* r, float4* z)
 		cudaError_t e = cudaStreamEndCapture(cap, &graph);
 		c->stream = saved;
 		if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;
+		if (rc == MAS_OK) rc = prioritize_apply_graph(c, graph);
 		if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&c->applyGraph, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
 		if (graph) cudaGraphDestroy(graph);
 		cudaStreamDestroy(cap);

@@ -21,6 +21,7 @@
 //
 // Every sum is evaluated in a fixed order (no float atomics): results are run-to-run deterministic.
 #include "mas_internal.h"
+#include <cstdlib>
 
 namespace mas {
 
@@ -168,25 +169,37 @@ __device__ __forceinline__ void group_sum_store(int key, Vec3 val, int lane, flo
 
 // BuildResidualHierarchy, level 0 -> 1 (cpp:1558-1574).  `send` (sharded contexts with attached peers): second copy of the
 // results in this rank's peer-readable send buffer, selected by the parity of the next apply counter.
+// The kernel is a chain of dependent loads (s2o -> r) per bank, so every warp carries kRestrictBanks banks with all their
+// loads in flight together: it heads the latency-bound coarse chain and shares the SMs with the streaming fine solve.
+constexpr int kRestrictBanks = 4;
 __global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const float4* __restrict__ r, const int* __restrict__ s2o,
 	const int* __restrict__ goingNext, int nv, int nVC, int bankBegin, int bankEnd, float4* __restrict__ coarseR,
 	float4* __restrict__ send, unsigned long long sendCap, const unsigned* epoch)
 {
 	const int lane = threadIdx.x & 31;
-	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	if (bank >= bankEnd) return;
-	const int v = bank * 32 + lane;
-	int key = -1;
-	Vec3 val = { 0.f, 0.f, 0.f };
-	if (v < nv)
+	const int bank0 = bankBegin + (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * kRestrictBanks;
+	if (bank0 >= bankEnd) return;
+	int ov[kRestrictBanks], key[kRestrictBanks];
+	float4 rv[kRestrictBanks];
+#pragma unroll
+	for (int k = 0; k < kRestrictBanks; ++k)
 	{
-		const float4 rv = r[s2o[v]];
-		val.x = rv.x; val.y = rv.y; val.z = rv.z;
-		key = goingNext[v];
+		const int v = (bank0 + k) * 32 + lane;
+		const bool live = bank0 + k < bankEnd && v < nv;
+		ov[k] = live ? s2o[v] : -1;
+		key[k] = live ? goingNext[v] : -1;
 	}
+#pragma unroll
+	for (int k = 0; k < kRestrictBanks; ++k) rv[k] = ov[k] >= 0 ? r[ov[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
 	float4* second = nullptr;
 	if (send) second = send + (unsigned long long)((*reinterpret_cast<const volatile unsigned*>(epoch) + 1u) & 1u) * sendCap;
-	group_sum_store(key, val, lane, coarseR, nVC, second);
+#pragma unroll
+	for (int k = 0; k < kRestrictBanks; ++k)
+	{
+		if (bank0 + k >= bankEnd) break;
+		const Vec3 val = { rv[k].x, rv[k].y, rv[k].z };
+		group_sum_store(key[k], val, lane, coarseR, nVC, second);
+	}
 }
 
 // ---- multi-GPU exchange over peer memory (NVLink) ---------------------------------------------------------------
@@ -195,10 +208,10 @@ __global__ void __launch_bounds__(kApplyThreads) restrict_fine_kernel(const floa
 // range (ids follow the Morton order of the fine banks) and have no other producer, so the exchange is an all-gather
 // without a reduction, done as a PULL:
 //   restrict_fine    writes its residuals to the local coarseR and to the local send buffer (plain local stores);
-//   signal_peers     one warp stores the apply counter into every rank's flag slot (the payload was completed by the
-//                    previous kernel, so the flag store itself carries no fence);
-//   gather_peers     wait (load-acquire) until all ranks have published this apply, then read the foreign slices
-//                    straight out of the peers' send buffers over NVLink into the local coarseR.
+//   gather_peers     stores the apply counter into every rank's flag slot (the payload was completed by the previous
+//                    kernel, so the flag store itself carries no fence), waits (load-acquire) until all ranks have
+//                    published this apply, then reads the foreign slices straight out of the peers' send buffers over
+//                    NVLink into the local coarseR.
 // No NCCL call, no host involvement, no remote stores of payload (a push variant needed a system-scope fence in every
 // storing CTA and cost 15-29 us per apply): the whole sharded apply stays one CUDA graph per rank.
 // Why two buffers are enough: a peer can only be one apply ahead of a rank it still has to hear from.
@@ -208,7 +221,8 @@ struct PeerArgs
 	float4* send[kMaxWorld];      // arena base of every rank (send buffer b at send[q] + b * cap)
 	unsigned* flags[kMaxWorld];   // flags array of every rank; slot [rank] is written by `rank`
 	int sliceBegin[kMaxWorld + 1];// level-1 slice (coarse index) produced by rank q: [sliceBegin[q], sliceBegin[q+1])
-	unsigned* epoch;              // local apply counter
+	unsigned* epoch;              // local apply counter (number of completed exchanges)
+	unsigned* ticket;             // local: blocks of gather_peers that have finished
 	unsigned* error;              // local sticky error flag (peer wait timed out)
 	unsigned long long cap;       // float4 elements per send buffer
 	int world, rank;
@@ -225,24 +239,19 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
 	return v;
 }
 
-// The residuals of this apply are complete in the local send buffer: they were written by the PREVIOUS kernel on this
-// stream, so they already sit in this GPU's L2 (the point of coherence for reads arriving over NVLink).  The flag store
-// therefore needs no fence of its own (a release store here costs a MEMBAR.SYS, ~5 us while the fine solve is streaming).
-__global__ void signal_peers_kernel(PeerArgs pa)
-{
-	const unsigned next = *reinterpret_cast<volatile unsigned*>(pa.epoch) + 1u;
-	if ((int)threadIdx.x < pa.world)
-		asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pa.flags[threadIdx.x] + pa.rank), "r"(next) : "memory");
-	__syncwarp();
-	if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(pa.epoch) = next;
-}
-
-// wait until every rank has published apply number *epoch, then pull the foreign level-1 slices into coarseR
+// Publish, wait, pull.  The residuals of this apply are complete in the local send buffer: they were written by the
+// PREVIOUS kernel on this stream, so they already sit in this GPU's L2 (the point of coherence for reads arriving over
+// NVLink).  The flag store therefore needs no fence of its own (a release store here costs a MEMBAR.SYS, ~5 us while the
+// fine solve is streaming).  Block 0 stores this apply's number into every rank's flag slot; every block then waits until
+// all ranks have published it and pulls its part of the foreign level-1 slices into coarseR.  The last block to finish
+// advances the local apply counter (all blocks have read it by then).
 constexpr int kGatherPerThread = 4;
 __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int first, int count, float4* __restrict__ coarseR)
 {
 	__shared__ int ok;
-	const unsigned want = *reinterpret_cast<volatile unsigned*>(pa.epoch);
+	const unsigned want = *reinterpret_cast<volatile unsigned*>(pa.epoch) + 1u;
+	if (blockIdx.x == 0 && (int)threadIdx.x < pa.world)
+		asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pa.flags[threadIdx.x] + pa.rank), "r"(want) : "memory");
 	if (threadIdx.x == 0) ok = 1;
 	__syncthreads();
 	if ((int)threadIdx.x < pa.world)
@@ -257,32 +266,44 @@ __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int firs
 		}
 	}
 	__syncthreads();
-	if (!ok) return;
-	const unsigned long long off = (unsigned long long)(want & 1u) * pa.cap;
-	const int stride = gridDim.x * blockDim.x;
-	for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < count; base += kGatherPerThread * stride)
+	if (ok)
 	{
-		// all remote loads of a thread are issued before the first one is consumed: one NVLink round trip, not one per element
-		const float4* src[kGatherPerThread];
-		float4 v[kGatherPerThread];
-#pragma unroll
-		for (int k = 0; k < kGatherPerThread; ++k)
+		const unsigned long long off = (unsigned long long)(want & 1u) * pa.cap;
+		const int stride = gridDim.x * blockDim.x;
+		for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < count; base += kGatherPerThread * stride)
 		{
-			const int i = first + base + k * stride;
-			src[k] = nullptr;
-			if (base + k * stride < count)
+			// all remote loads of a thread are issued before the first one is consumed: one NVLink round trip, not one per element
+			const float4* src[kGatherPerThread];
+			float4 v[kGatherPerThread];
+#pragma unroll
+			for (int k = 0; k < kGatherPerThread; ++k)
 			{
-				int q = 0;
-				while (q + 1 < pa.world && i >= pa.sliceBegin[q + 1]) ++q;
-				if (q != pa.rank) src[k] = pa.send[q] + off + i;
+				const int i = first + base + k * stride;
+				src[k] = nullptr;
+				if (base + k * stride < count)
+				{
+					int q = 0;
+					while (q + 1 < pa.world && i >= pa.sliceBegin[q + 1]) ++q;
+					if (q != pa.rank) src[k] = pa.send[q] + off + i;
+				}
 			}
+#pragma unroll
+			for (int k = 0; k < kGatherPerThread; ++k)
+				if (src[k]) v[k] = __ldcg(src[k]);   // written by another GPU: read at the owner's L2, never from this SM's L1
+#pragma unroll
+			for (int k = 0; k < kGatherPerThread; ++k)
+				if (src[k]) coarseR[first + base + k * stride] = v[k];
 		}
-#pragma unroll
-		for (int k = 0; k < kGatherPerThread; ++k)
-			if (src[k]) v[k] = __ldcg(src[k]);   // written by another GPU: read at the owner's L2, never from this SM's L1
-#pragma unroll
-		for (int k = 0; k < kGatherPerThread; ++k)
-			if (src[k]) coarseR[first + base + k * stride] = v[k];
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+		if (atomicAdd(pa.ticket, 1u) == gridDim.x - 1)
+		{
+			*reinterpret_cast<volatile unsigned*>(pa.ticket) = 0u;
+			*reinterpret_cast<volatile unsigned*>(pa.epoch) = want;
+		}
 	}
 }
 
@@ -442,6 +463,7 @@ __global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int
 
 // SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ.
 // addCoarse = 0: the coarse levels are not ready (or absent); z holds the level-0 part only.
+// One warp per bank.
 __global__ void __launch_bounds__(kApplyThreads, 8) solve_fine_kernel(const float* __restrict__ packed,
 	const float4* __restrict__ r, const int* __restrict__ s2o, const int* __restrict__ goingNext,
 	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int packedBankBase, int addCoarse, float4* __restrict__ z)
@@ -507,6 +529,7 @@ static PeerArgs peer_args(const Context* c)
 	for (int q = 0; q <= c->world; ++q) pa.sliceBegin[q] = c->levelSize[1][1] - c->nVC + c->l1Slice[q];
 	unsigned* ctl = reinterpret_cast<unsigned*>((unsigned char*)c->peerArena[c->rank] + 2 * sizeof(float4) * c->arenaCap);
 	pa.epoch = ctl + kMaxWorld;
+	pa.ticket = ctl + kMaxWorld + 1;
 	pa.error = ctl + kMaxWorld + 2;
 	pa.cap = c->arenaCap;
 	pa.world = c->world;
@@ -527,14 +550,9 @@ int apply_begin(Context* c, const float4* r)
 	if (c->p2p) pa = peer_args(c);
 	if (ownBanks > 0)
 	{
-		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
+		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta * kRestrictBanks), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
 			c->ownFineBegin, c->ownFineEnd, c->coarseR.p, c->p2p ? pa.send[c->rank] : nullptr, c->p2p ? pa.cap : 0ull,
 			c->p2p ? pa.epoch : nullptr);
-		c->applyLaunches += 1;
-	}
-	if (c->p2p)
-	{
-		signal_peers_kernel<<<1, 32, 0, st>>>(pa);
 		c->applyLaunches += 1;
 	}
 	return MAS_OK;
@@ -631,6 +649,12 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 			head = (int)(2400 + 8 * ownVerts / 2000);
 			if (c->p2p) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
 		}
+		// The CTA dispatcher works through grids in launch order, and stream / node priority does not let a later grid overtake
+		// the not-yet-dispatched CTAs of an earlier one (measured: beside a head of more than one wave, 148 x 8 CTAs, every
+		// chain kernel waited 20-26 us until the head's last CTA had been dispatched).  The head therefore never exceeds one
+		// wave minus room for the chain's own CTAs: it is resident in full right away and the chain is dispatched beside it.
+		const int cap = (c->smCount * 8 - 80) * kWarpsPerCta;
+		if (head > cap) head = cap;
 		head = (head + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
 		if (head > ownBanks) head = ownBanks;
 	}
@@ -671,6 +695,32 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 	}
 	MAS_CUDA(c, cudaStreamWaitEvent(st, c->evTail, 0));
 	MAS_CUDA(c, cudaGetLastError());
+	return MAS_OK;
+}
+
+// Kernel nodes of the captured apply graph: the latency-bound coarse chain gets the highest launch priority, the two
+// streaming kernels (level-0 solve, coarse addition) the lowest, so that a chain kernel's few CTAs are dispatched as soon as
+// any CTA slot frees up instead of queueing behind the not-yet-dispatched CTAs of the concurrent level-0 solve.
+int prioritize_apply_graph(Context* c, cudaGraph_t graph)
+{
+	int prLow = 0, prHigh = 0;
+	MAS_CUDA(c, cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+	size_t n = 0;
+	MAS_CUDA(c, cudaGraphGetNodes(graph, nullptr, &n));
+	std::vector<cudaGraphNode_t> nodes(n);
+	if (n) MAS_CUDA(c, cudaGraphGetNodes(graph, nodes.data(), &n));
+	for (size_t i = 0; i < n; ++i)
+	{
+		cudaGraphNodeType type;
+		MAS_CUDA(c, cudaGraphNodeGetType(nodes[i], &type));
+		if (type != cudaGraphNodeTypeKernel) continue;
+		cudaKernelNodeParams kp;
+		MAS_CUDA(c, cudaGraphKernelNodeGetParams(nodes[i], &kp));
+		const bool streaming = kp.func == (void*)solve_fine_kernel || kp.func == (void*)add_coarse_kernel;
+		cudaKernelNodeAttrValue v;
+		v.priority = streaming ? prLow : prHigh;
+		MAS_CUDA(c, cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v));
+	}
 	return MAS_OK;
 }
 

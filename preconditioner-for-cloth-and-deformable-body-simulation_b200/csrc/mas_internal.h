@@ -220,6 +220,7 @@ int unpack_dense_inverse(Context* c, int block, float* hostOut);                
 int apply_begin(Context* c, const float4* r);                                                     // mas_apply.cu
 int apply_end(Context* c, const float4* r, float4* z);                                            // mas_apply.cu
 int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st);                        // mas_apply.cu
+int prioritize_apply_graph(Context* c, cudaGraph_t graph);                                        // mas_apply.cu
 int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges, const int* idx, const float4* b, float4* x,
 	float relTol, int maxIter, int usePrecond, int* itersOut, float* relResOut);                  // mas_pcg.cu
 

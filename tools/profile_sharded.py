@@ -11,7 +11,7 @@ torch.cuda.set_device(local)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-mesh = S.cloth(int(os.environ.get("MAS_N", 1024)))
+mesh = S.cloth_rect(int(os.environ.get("MAS_NX", os.environ.get("MAS_N", 1024))), int(os.environ.get("MAS_NY", os.environ.get("MAS_N", 1024))))
 g = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=torch.cuda.current_stream())
 if len(sys.argv) > 1:
     g.set_option(1, int(sys.argv[1]))
