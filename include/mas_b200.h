@@ -93,7 +93,8 @@ enum
 	MAS_INT_PREPARE_LAUNCHES = 10, /* kernels launched by the last mas_prepare */
 	MAS_INT_PCG_LAUNCHES_PER_ITER = 11, /* kernels per iteration of the last mas_pcg_solve (its own 4 + the apply's) */
 	MAS_INT_PCG_CONVERGED = 12,    /* 1 if the last mas_pcg_solve met its tolerance */
-	MAS_INT_PEER_ERROR = 13        /* 1 if a peer-memory wait ever timed out (a rank stopped publishing) */
+	MAS_INT_PEER_ERROR = 13,       /* 1 if a peer-memory wait ever timed out (a rank stopped publishing) */
+	MAS_INT_ALIGNED_CUTS = 14      /* sharded contexts: 1 if no level-1 bank straddles a shard cut (the apply exchanges level-2 residuals) */
 };
 
 /* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */

@@ -76,7 +76,7 @@ static void free_all(Context* c)
 {
 	drop_graph(c);
 	close_peers(c);
-	release(c->arena);
+	release(c->arena); release(c->cutInfo);
 	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
 	release(c->aabb); release(c->code); release(c->codeSorted); release(c->s2o); release(c->o2s); release(c->iota);
 	release(c->adjStart); release(c->adjIdx); release(c->cubTemp);
@@ -515,6 +515,7 @@ int mas_get_int(mas_handle_t h, int key, long long* out)
 	case MAS_INT_PREPARE_LAUNCHES: *out = c->prepareLaunches; break;
 	case MAS_INT_PCG_LAUNCHES_PER_ITER: *out = c->pcgLaunchesPerIter; break;
 	case MAS_INT_PCG_CONVERGED: *out = c->pcgConverged; break;
+	case MAS_INT_ALIGNED_CUTS: *out = c->alignedCuts ? 1 : 0; break;
 	case MAS_INT_PEER_ERROR:
 	{
 		*out = 0;

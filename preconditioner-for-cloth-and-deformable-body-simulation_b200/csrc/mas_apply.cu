@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int firs
 // One 32-node group of coarse nodes [begin + 32*bank, ...): sum R over the nodes that share a parent and store it
 // (BuildResidualHierarchy level l -> l+1, cpp:1577-1591)
 __device__ __forceinline__ void restrict_bank(const int* __restrict__ goingNext, int begin, int count, int bank, int nVC,
-	float4* __restrict__ coarseR, int lane, const float4 rv)
+	float4* __restrict__ coarseR, int lane, const float4 rv, float4* __restrict__ second = nullptr)
 {
 	const int local = bank * 32 + lane;
 	int key = -1;
@@ -320,20 +320,24 @@ __device__ __forceinline__ void restrict_bank(const int* __restrict__ goingNext,
 		val.x = rv.x; val.y = rv.y; val.z = rv.z;
 		key = goingNext[begin + local];
 	}
-	group_sum_store(key, val, lane, coarseR, nVC);
+	group_sum_store(key, val, lane, coarseR, nVC, second);
 }
 
-// BuildResidualHierarchy, level 1 -> 2 (cpp:1577-1591): one warp per 32 level-1 nodes
+// BuildResidualHierarchy, level 1 -> 2 (cpp:1577-1591): one warp per 32 level-1 nodes, banks [bankBegin, bankEnd).
+// `send`: see restrict_fine_kernel (sharded contexts with aligned cuts publish their level-2 residuals instead).
 __global__ void __launch_bounds__(kApplyThreads) restrict_l1_kernel(const int* __restrict__ goingNext, int begin, int count,
-	int nVC, float4* __restrict__ coarseR)
+	int nVC, int bankBegin, int bankEnd, float4* __restrict__ coarseR, float4* __restrict__ send, unsigned long long sendCap,
+	const unsigned* epoch)
 {
 	const int lane = threadIdx.x & 31;
-	const int bank = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	if (bank * 32 >= count) return;
+	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (bank >= bankEnd || bank * 32 >= count) return;
 	const int local = bank * 32 + lane;
 	float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (local < count) rv = coarseR[begin - nVC + local];
-	restrict_bank(goingNext, begin, count, bank, nVC, coarseR, lane, rv);
+	float4* second = nullptr;
+	if (send) second = send + (unsigned long long)((*reinterpret_cast<const volatile unsigned*>(epoch) + 1u) & 1u) * sendCap;
+	restrict_bank(goingNext, begin, count, bank, nVC, coarseR, lane, rv, second);
 }
 
 // Levels >= 2 hold a few thousand nodes at most: one CTA walks the remaining restrictions level by level.
@@ -343,18 +347,25 @@ struct TopArgs
 	int count[kMaxLevel + 1], begin[kMaxLevel + 1];
 };
 constexpr int kTopThreads = 1024;
+constexpr int kTopBanks = 4;   // banks a warp carries per round, loads in flight together
 __global__ void __launch_bounds__(kTopThreads) restrict_top_kernel(const int* __restrict__ goingNext, TopArgs a, float4* __restrict__ coarseR)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = kTopThreads / 32;
 	for (int level = 2; level + 1 < a.numLevel; ++level)
 	{
 		const int banks = (a.count[level] + 31) >> 5;
-		for (int bank = warp; bank < banks; bank += nWarps)
+		for (int bank0 = warp * kTopBanks; bank0 < banks; bank0 += nWarps * kTopBanks)
 		{
-			const int local = bank * 32 + lane;
-			float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (local < a.count[level]) rv = coarseR[a.begin[level] - a.nVC + local];
-			restrict_bank(goingNext, a.begin[level], a.count[level], bank, a.nVC, coarseR, lane, rv);
+			float4 rv[kTopBanks];
+#pragma unroll
+			for (int k = 0; k < kTopBanks; ++k)
+			{
+				const int local = (bank0 + k) * 32 + lane;
+				rv[k] = local < a.count[level] ? coarseR[a.begin[level] - a.nVC + local] : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+#pragma unroll
+			for (int k = 0; k < kTopBanks; ++k)
+				if (bank0 + k < banks) restrict_bank(goingNext, a.begin[level], a.count[level], bank0 + k, a.nVC, coarseR, lane, rv[k]);
 		}
 		__threadfence_block();
 		__syncthreads();
@@ -515,6 +526,10 @@ static int prolonged_top(const Context* c)
 	return c->optProlongAll ? c->numLevel : (c->numLevel < 4 ? c->numLevel : 4);
 }
 
+// Sharded context whose cuts are aligned to level-1 banks: every rank restricts its own level-1 banks to level 2 and the
+// exchange carries level-2 residuals.  (With two levels there is nothing to exchange at all.)
+static bool exchange_level2(const Context* c) { return c->world > 1 && c->alignedCuts; }
+
 static PeerArgs peer_args(const Context* c)
 {
 	PeerArgs pa;
@@ -526,7 +541,10 @@ static PeerArgs peer_args(const Context* c)
 		pa.send[q] = reinterpret_cast<float4*>(base);
 		pa.flags[q] = reinterpret_cast<unsigned*>(base + 2 * sizeof(float4) * c->arenaCap);
 	}
-	for (int q = 0; q <= c->world; ++q) pa.sliceBegin[q] = c->levelSize[1][1] - c->nVC + c->l1Slice[q];
+	// what the peers pull: level-1 residuals (cuts not aligned) or level-2 residuals (aligned cuts), as coarse indices
+	const bool l2x = exchange_level2(c);
+	for (int q = 0; q <= c->world; ++q)
+		pa.sliceBegin[q] = l2x ? c->levelSize[2][1] - c->nVC + c->l2Slice[q] : c->levelSize[1][1] - c->nVC + c->l1Slice[q];
 	unsigned* ctl = reinterpret_cast<unsigned*>((unsigned char*)c->peerArena[c->rank] + 2 * sizeof(float4) * c->arenaCap);
 	pa.epoch = ctl + kMaxWorld;
 	pa.ticket = ctl + kMaxWorld + 1;
@@ -546,12 +564,23 @@ int apply_begin(Context* c, const float4* r)
 	{
 		MAS_CUDA(c, cudaMemsetAsync(c->coarseR.p, 0, sizeof(float4) * (size_t)c->nCoarseNodes, st));
 	}
+	const bool l2x = exchange_level2(c);
 	PeerArgs pa;
 	if (c->p2p) pa = peer_args(c);
 	if (ownBanks > 0)
 	{
+		const bool publish = c->p2p && !l2x;
 		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta * kRestrictBanks), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
-			c->ownFineBegin, c->ownFineEnd, c->coarseR.p, c->p2p ? pa.send[c->rank] : nullptr, c->p2p ? pa.cap : 0ull,
+			c->ownFineBegin, c->ownFineEnd, c->coarseR.p, publish ? pa.send[c->rank] : nullptr, publish ? pa.cap : 0ull,
+			publish ? pa.epoch : nullptr);
+		c->applyLaunches += 1;
+	}
+	if (l2x && c->numLevel > 2 && c->l1BlockEnd > c->l1BlockBegin)
+	{
+		// own level-1 banks -> level 2 (complete: no level-1 bank straddles a cut); published for the peers
+		const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
+		restrict_l1_kernel<<<cdiv(c->l1BlockEnd - c->l1BlockBegin, kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC,
+			c->l1BlockBegin, c->l1BlockEnd, c->coarseR.p, c->p2p ? pa.send[c->rank] : nullptr, c->p2p ? pa.cap : 0ull,
 			c->p2p ? pa.epoch : nullptr);
 		c->applyLaunches += 1;
 	}
@@ -564,17 +593,21 @@ static int launch_coarse(Context* c, cudaStream_t st)
 	if (c->numLevel < 2) return MAS_OK;
 	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
 	const int nCoarseBlocks = c->nCoarseNodes / 32;
-	if (c->p2p)
+	const bool l2x = exchange_level2(c);
+	if (c->p2p && !(l2x && c->numLevel < 3))
 	{
-		int grid = cdiv(cnt1, 256 * kGatherPerThread);
+		const int first = l2x ? c->levelSize[2][1] - c->nVC : begin1 - c->nVC;
+		const int count = l2x ? c->levelSize[2][0] : cnt1;
+		int grid = cdiv(count, 256 * kGatherPerThread);
 		if (grid > 128) grid = 128;
 		if (grid < 1) grid = 1;
-		gather_peers_kernel<<<grid, 256, 0, st>>>(peer_args(c), begin1 - c->nVC, cnt1, c->coarseR.p);
+		gather_peers_kernel<<<grid, 256, 0, st>>>(peer_args(c), first, count, c->coarseR.p);
 		c->applyLaunches += 1;
 	}
-	if (c->numLevel > 2)
+	if (c->numLevel > 2 && !l2x)
 	{
-		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, c->coarseR.p);
+		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, 0,
+			cdiv(cnt1, 32), c->coarseR.p, nullptr, 0ull, nullptr);
 		c->applyLaunches += 1;
 	}
 	if (c->numLevel > 3)

@@ -299,6 +299,30 @@ __global__ void coarse_tables_kernel(const int* __restrict__ goingNext, int nv, 
 	out[v] = make_int4(t[0], t[1], t[2], t[3]);
 }
 
+// Shard cut q+1 (block q): the fine bank nearest to the even split nFine*(q+1)/world, within +-window banks, at which the
+// exclusive level-1 id prefix is a multiple of 32 (no level-1 bank straddles the cut).  out[q+1] = bank, out[16+q+1] = 1 if
+// aligned, out[32+q+1] = level-1 id at the cut.  No such bank: the even split, flagged unaligned.
+__global__ void find_cuts_kernel(const int* __restrict__ bankPrefix, int nBanks, int nFine, int total, int world, int window,
+	int* __restrict__ out)
+{
+	__shared__ unsigned long long best;
+	const int q = blockIdx.x + 1;
+	const int ideal = (int)((long long)nFine * q / world);
+	if (threadIdx.x == 0) best = ~0ull;
+	__syncthreads();
+	const int lo = max(1, ideal - window), hi = min(nBanks - 1, ideal + window);
+	for (int b = lo + (int)threadIdx.x; b <= hi; b += blockDim.x)
+		if ((bankPrefix[b] & 31) == 0)
+			atomicMin(&best, ((unsigned long long)(unsigned)abs(b - ideal) << 32) | (unsigned)b);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		if (ideal >= nBanks) { out[q] = ideal; out[16 + q] = 1; out[32 + q] = total; }        // nothing but padding behind the cut
+		else if (best != ~0ull) { const int b = (int)(best & 0xffffffffu); out[q] = b; out[16 + q] = 1; out[32 + q] = bankPrefix[b]; }
+		else { out[q] = ideal; out[16 + q] = 0; out[32 + q] = bankPrefix[ideal]; }
+	}
+}
+
 }  // namespace
 
 int launch_exclusive_scan(Context* c, const int* in, int count, int* out, int* totalOut)
@@ -399,19 +423,41 @@ int build_hierarchy(Context* c)
 	c->levelSize[1][0] = n1;
 	c->levelSize[1][1] = nVC;
 	// level-1 ids are handed out in Morton order of the fine banks, so the level-1 nodes produced by rank q's banks are the
-	// contiguous range [bankPrefix[firstBank(q)], bankPrefix[firstBank(q+1)]) — the slice its peers pull from it
+	// contiguous range [bankPrefix[firstBank(q)], bankPrefix[firstBank(q+1)]) — the slice its peers pull from it.  The cuts
+	// themselves are chosen here (every rank computes the same ones): see Context::alignedCuts.
 	for (int q = 0; q <= 16; ++q) c->l1Slice[q] = n1;
 	c->l1Slice[0] = 0;
+	c->alignedCuts = false;
 	if (c->world > 1)
 	{
 		const int nBanks = (nv + 31) / 32, nFine = nVC / 32;
-		for (int q = 1; q < c->world; ++q)
-		{
-			const int firstBank = (int)((long long)nFine * q / c->world);
-			if (firstBank < nBanks)
-				MAS_CUDA(c, cudaMemcpyAsync(&c->l1Slice[q], c->bankPrefix.p + firstBank, sizeof(int), cudaMemcpyDeviceToHost, s));
-		}
+		int window = nFine / (8 * c->world);
+		if (window < 32) window = 32;
+		if (int rc = reserve(c, c->cutInfo, 48)) return rc;
+		find_cuts_kernel<<<c->world - 1, 256, 0, s>>>(c->bankPrefix.p, nBanks, nFine, n1, c->world, window, c->cutInfo.p);
+		c->prepareLaunches += 1;
+		int info[48];
+		MAS_CUDA(c, cudaMemcpyAsync(info, c->cutInfo.p, sizeof(info), cudaMemcpyDeviceToHost, s));
 		MAS_CUDA(c, cudaStreamSynchronize(s));
+		info[0] = 0; info[c->world] = nFine;
+		bool aligned = true, ordered = true;
+		for (int q = 1; q < c->world; ++q) { aligned = aligned && info[16 + q]; ordered = ordered && info[q] >= info[q - 1] && info[q] <= nFine; }
+		if (!ordered)
+		{
+			// windows overlap only on meshes of a few banks per shard: fall back to the even split
+			aligned = false;
+			for (int q = 1; q < c->world; ++q)
+			{
+				info[q] = (int)((long long)nFine * q / c->world);
+				if (info[q] < nBanks) MAS_CUDA(c, cudaMemcpyAsync(&info[32 + q], c->bankPrefix.p + info[q], sizeof(int), cudaMemcpyDeviceToHost, s));
+				else info[32 + q] = n1;
+			}
+			MAS_CUDA(c, cudaStreamSynchronize(s));
+		}
+		for (int q = 1; q < c->world; ++q) c->l1Slice[q] = info[32 + q];
+		c->ownFineBegin = info[c->rank];
+		c->ownFineEnd = info[c->rank + 1];
+		c->alignedCuts = aligned;
 	}
 	c->nL1Blocks = pad32(n1) / 32;
 	c->l1BlockBegin = 0;
@@ -443,6 +489,20 @@ int build_hierarchy(Context* c)
 		if (int rc = number_level(c, c->nextMask.p, cnt, 1, begin, c->nextId.p, &nNext)) return rc;
 		c->levelSize[level + 1][0] = nNext;
 		c->levelSize[level + 1][1] = begin + pad32(cnt);
+		if (level == 1 && c->world > 1 && c->alignedCuts)
+		{
+			// level-2 ids follow the level-1 banks in order: rank q's level-1 banks [l1Slice[q]/32, l1Slice[q+1]/32) produce the
+			// level-2 nodes [bankPrefix[l1Slice[q]/32], bankPrefix[l1Slice[q+1]/32))
+			const int nL1Banks = (cnt + 31) / 32;
+			for (int q = 0; q <= 16; ++q) c->l2Slice[q] = nNext;
+			c->l2Slice[0] = 0;
+			for (int q = 1; q < c->world; ++q)
+			{
+				const int bank = c->l1Slice[q] / 32;
+				if (bank < nL1Banks) MAS_CUDA(c, cudaMemcpyAsync(&c->l2Slice[q], c->bankPrefix.p + bank, sizeof(int), cudaMemcpyDeviceToHost, s));
+			}
+			MAS_CUDA(c, cudaStreamSynchronize(s));
+		}
 		next_level_table_kernel<<<cdiv(nv, threads), threads, 0, s>>>(c->cst[level - 1].p, c->nextId.p, nv, c->cst[level].p);
 		c->prepareLaunches += 1;
 	}

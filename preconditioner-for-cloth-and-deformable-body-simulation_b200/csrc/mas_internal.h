@@ -171,6 +171,13 @@ struct Context
 	// Coarse blocks this rank inverts and solves: the level-1 blocks [l1BlockBegin, l1BlockEnd) that hold its own level-1
 	// nodes (a block straddling two shards is done by both) plus every block of levels >= 2, [nL1Blocks, nCoarseBlocks).
 	int l1BlockBegin = 0, l1BlockEnd = 0, nL1Blocks = 0;
+	// Shard cuts are moved (within +-1/8 of a shard) to fine banks where the running level-1 id is a multiple of 32, so that
+	// no level-1 bank straddles two shards.  When every cut could be aligned, a rank restricts its own level-1 banks to
+	// level 2 by itself and the per-apply exchange shrinks to the level-2 residuals (nv/1024 nodes instead of nv/32);
+	// l2Slice[q] = first level-2 node (level-local id) produced by rank q's level-1 banks.
+	bool alignedCuts = false;
+	int l2Slice[17] = {};
+	DevBuf<int> cutInfo;               // [3 * 16]: chosen cut bank, aligned flag, level-1 id at the cut
 
 	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
 	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)

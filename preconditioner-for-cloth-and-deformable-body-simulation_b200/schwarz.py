@@ -23,7 +23,7 @@ MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
 OPT_PROLONG_ALL_LEVELS, OPT_APPLY_VARIANT, OPT_USE_GRAPH, OPT_TIME_KERNELS = 0, 1, 2, 3
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
  INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
- INT_PCG_CONVERGED, INT_PEER_ERROR) = range(14)
+ INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS) = range(15)
 (ARR_MORTON, ARR_SORTED_GET_ORIGINAL, ARR_ORIGINAL_GET_SORTED, ARR_GOING_NEXT, ARR_LEVEL_SIZE, ARR_FINE_CONNECT_MASK,
  ARR_COARSE_SPACE_TABLE, ARR_COARSE_TABLES, ARR_SORTED_ADJ_STARTS, ARR_SORTED_ADJ_IDX, ARR_STENCILS,
  ARR_STENCIL_INDEX_MAPPED, ARR_DENSE_INVERSE, ARR_MAPPED_R, ARR_MAPPED_Z, ARR_AABB) = range(16)
@@ -248,6 +248,9 @@ class SeSchwarzPreconditioner:
 
     @property
     def peer_error(self): return self.get_int(INT_PEER_ERROR)
+
+    @property
+    def aligned_cuts(self): return bool(self.get_int(INT_ALIGNED_CUTS))
 
     # ---- introspection (parity tests)
     def get_int(self, key: int) -> int:

@@ -62,6 +62,8 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
     for g in shards:
         assert np.array_equal(g.going_next(), single.going_next())
         assert np.array_equal(g.level_size(), single.level_size())
+    # both exchange protocols are exercised: level-2 residuals when every cut falls between level-1 banks, else level 1
+    assert all(g.aligned_cuts for g in shards) == (name in ("cloth_rect512x256", "cloth256")), [g.aligned_cuts for g in shards]
 
     zs = [torch.full_like(r, float("nan")) for _ in shards]
     for g in shards:

@@ -11,11 +11,11 @@ torch.cuda.set_device(local)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-mesh = S.cloth_rect(int(os.environ.get("MAS_NX", os.environ.get("MAS_N", 1024))), int(os.environ.get("MAS_NY", os.environ.get("MAS_N", 1024))))
+mesh = S.cloth_rect_device(int(os.environ.get("MAS_NX", os.environ.get("MAS_N", 1024))), int(os.environ.get("MAS_NY", os.environ.get("MAS_N", 1024))), torch.device(f"cuda:{local}"))
 g = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=torch.cuda.current_stream())
 if len(sys.argv) > 1:
     g.set_option(1, int(sys.argv[1]))
-t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+t = lambda a: a.cuda() if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).cuda()
 g.m_positions, g.m_neighbours = t(mesh.positions), (t(mesh.nbr_starts), t(mesh.nbr_idx))
 g.AllocatePrecoditioner(mesh.nv, 0, 0)
 d = (t(mesh.diag), t(mesh.offdiag), t(mesh.nbr_starts))
@@ -38,14 +38,15 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-if rank == 0:
-    path = os.path.join(ROOT, "gpurun_out", f"trace_w{world}.json")
+if rank in (0, world - 1):
+    path = os.path.join(ROOT, "gpurun_out", f"trace_w{world}_r{rank}.json")
     prof.export_chrome_trace(path)
     ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
     ev.sort(key=lambda e: e["ts"])
     # split into steps at restrict_fine / first kernel of each graph launch
     names = [e["name"].split("(")[0].split("::")[-1] for e in ev]
     per = len(ev) // 10
+    print(f"---- rank {rank}")
     step = ev[per * 5: per * 6]
     t0 = min(e["ts"] for e in step)
     for e in step:
