@@ -366,6 +366,22 @@ def run_ours(args):
         fine_ms = sum(acc) / len(acc)
         fine_ms_med = acc[len(acc) // 2]
 
+    # ---- sharded runs: every rank's own level-0 kernel time (same banks per rank), to tell GPU-to-GPU spread from exchange cost
+    per_rank_fine_ms = None
+    if world > 1 and p2p and not args.lean:
+        g.set_option(3, 1)
+        for _ in range(3):
+            g.Preconditioning(z, r)
+        acc = []
+        for _ in range(30):
+            g.Preconditioning(z, r)
+            acc.append(g.timing_ms(2))
+        g.set_option(3, 0)
+        mine = torch.tensor([sum(acc) / len(acc)], device=dev, dtype=torch.float64)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank_fine_ms = [round(float(x.item()), 5) for x in gathered]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -429,7 +445,9 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "whole sharded apply, rank 0 share (level-0 solve dominates)",
                 "achieved": rank_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": rank_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(rank_bytes), "traffic": None}
+                "algorithmic_bytes_per_launch": int(rank_bytes), "traffic": None,
+                "per_rank_fine_kernel_ms": per_rank_fine_ms,
+                "aligned_cuts": g.aligned_cuts}
     out = {
         "metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -74,7 +74,11 @@ enum
 	MAS_OPT_USE_GRAPH = 2,
 	/* 1: bracket the dominant apply kernel (level-0 solve) with CUDA events on the launching stream so that
 	 * mas_get_timing(h, 2, ..) reports its duration; implies un-captured launches.  Default 0. */
-	MAS_OPT_TIME_KERNELS = 3
+	MAS_OPT_TIME_KERNELS = 3,
+	/* sharded contexts, 1 (default): move every shard cut (by at most 1/8 of a shard) to a fine bank where the running
+	 * level-1 id is a multiple of 32, so that no level-1 bank straddles two shards and the per-apply exchange carries
+	 * level-2 residuals; 0: even split, exchange of level-1 residuals.  Takes effect at the next mas_prepare. */
+	MAS_OPT_ALIGN_CUTS = 4
 };
 
 /* mas_get_int keys */

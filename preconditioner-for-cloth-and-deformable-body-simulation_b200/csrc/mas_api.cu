@@ -173,6 +173,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_APPLY_VARIANT: h->optApplyVariant = value; break;
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
+	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; break;
 	default: return fail(h, MAS_ERR_INVALID, "unknown option");
 	}
 	drop_graph(h);

@@ -340,32 +340,26 @@ __global__ void __launch_bounds__(kApplyThreads) restrict_l1_kernel(const int* _
 	restrict_bank(goingNext, begin, count, bank, nVC, coarseR, lane, rv, second);
 }
 
-// Levels >= 2 hold a few thousand nodes at most: one CTA walks the remaining restrictions level by level.
+// The top levels hold a few hundred nodes: one CTA walks the remaining restrictions level by level, starting at
+// firstLevel (level 2, or level 3 when level 2 is large enough to deserve the multi-CTA kernel above).
 struct TopArgs
 {
-	int numLevel, nVC;
+	int numLevel, nVC, firstLevel;
 	int count[kMaxLevel + 1], begin[kMaxLevel + 1];
 };
-constexpr int kTopThreads = 1024;
-constexpr int kTopBanks = 4;   // banks a warp carries per round, loads in flight together
+constexpr int kTopThreads = 256;    // small enough to be resident beside the persistent level-0 kernel (registers)
 __global__ void __launch_bounds__(kTopThreads) restrict_top_kernel(const int* __restrict__ goingNext, TopArgs a, float4* __restrict__ coarseR)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = kTopThreads / 32;
-	for (int level = 2; level + 1 < a.numLevel; ++level)
+	for (int level = a.firstLevel; level + 1 < a.numLevel; ++level)
 	{
 		const int banks = (a.count[level] + 31) >> 5;
-		for (int bank0 = warp * kTopBanks; bank0 < banks; bank0 += nWarps * kTopBanks)
+		for (int bank = warp; bank < banks; bank += nWarps)
 		{
-			float4 rv[kTopBanks];
-#pragma unroll
-			for (int k = 0; k < kTopBanks; ++k)
-			{
-				const int local = (bank0 + k) * 32 + lane;
-				rv[k] = local < a.count[level] ? coarseR[a.begin[level] - a.nVC + local] : make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-#pragma unroll
-			for (int k = 0; k < kTopBanks; ++k)
-				if (bank0 + k < banks) restrict_bank(goingNext, a.begin[level], a.count[level], bank0 + k, a.nVC, coarseR, lane, rv[k]);
+			const int local = bank * 32 + lane;
+			float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (local < a.count[level]) rv = coarseR[a.begin[level] - a.nVC + local];
+			restrict_bank(goingNext, a.begin[level], a.count[level], bank, a.nVC, coarseR, lane, rv);
 		}
 		__threadfence_block();
 		__syncthreads();
@@ -613,11 +607,23 @@ static int launch_coarse(Context* c, cudaStream_t st)
 	if (c->numLevel > 3)
 	{
 		TopArgs a;
-		a.numLevel = c->numLevel; a.nVC = c->nVC;
+		a.numLevel = c->numLevel; a.nVC = c->nVC; a.firstLevel = 2;
 		for (int l = 0; l <= kMaxLevel; ++l) { a.count[l] = 0; a.begin[l] = 0; }
 		for (int l = 1; l <= c->numLevel; ++l) { a.count[l] = c->levelSize[l][0]; a.begin[l] = c->levelSize[l][1]; }
-		restrict_top_kernel<<<1, kTopThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p);
-		c->applyLaunches += 1;
+		const int cnt2 = c->levelSize[2][0];
+		if (cnt2 > 2048)
+		{
+			// a large level 2 (meshes beyond ~2M vertices): level 2 -> 3 on many CTAs, the single CTA takes over from level 3
+			restrict_l1_kernel<<<cdiv(cdiv(cnt2, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, c->levelSize[2][1], cnt2, c->nVC, 0,
+				cdiv(cnt2, 32), c->coarseR.p, nullptr, 0ull, nullptr);
+			c->applyLaunches += 1;
+			a.firstLevel = 3;
+		}
+		if (a.firstLevel + 1 < c->numLevel)
+		{
+			restrict_top_kernel<<<1, kTopThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p);
+			c->applyLaunches += 1;
+		}
 	}
 	// level-1 blocks stay partitioned (each rank solves the blocks that hold its own level-1 nodes); levels >= 2 are solved
 	// redundantly on every rank, which removes any exchange of z

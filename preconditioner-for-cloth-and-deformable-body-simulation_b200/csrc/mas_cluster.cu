@@ -442,9 +442,9 @@ int build_hierarchy(Context* c)
 		info[0] = 0; info[c->world] = nFine;
 		bool aligned = true, ordered = true;
 		for (int q = 1; q < c->world; ++q) { aligned = aligned && info[16 + q]; ordered = ordered && info[q] >= info[q - 1] && info[q] <= nFine; }
-		if (!ordered)
+		if (!ordered || !c->optAlignCuts)
 		{
-			// windows overlap only on meshes of a few banks per shard: fall back to the even split
+			// windows overlap only on meshes of a few banks per shard (or alignment is switched off): the even split
 			aligned = false;
 			for (int q = 1; q < c->world; ++q)
 			{

@@ -94,6 +94,7 @@ struct Context
 	int optApplyVariant = -1;    // fine banks solved concurrently with the coarse chain: -1 auto, 0 none, >0 per-mille of the owned banks
 	int optUseGraph = 1;
 	int optTimeKernels = 0;
+	int optAlignCuts = 1;
 	int rank = 0, world = 1;
 	int smCount = 148;
 

@@ -33,9 +33,10 @@ def _mesh(synth, name):
     raise KeyError(name)
 
 
+@pytest.mark.parametrize("align", [1, 0])
 @pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth50_ragged", 3), ("cloth256", 4),
                                         ("cloth_rect512x256", 8), ("cloth_rect512x256", 3)])
-def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
+def test_shards_in_one_process_match_single_device(name, world, align, pkg, synth):
     import torch
     mesh = _mesh(synth, name)
     r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
@@ -50,6 +51,7 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
              st=dev(mesh.nbr_starts), ix=dev(mesh.nbr_idx), diag=dev(mesh.diag), off=dev(mesh.offdiag),
              ef=raw(mesh.ef) if mesh.ef.size else None, ee=raw(mesh.ee) if mesh.ee.size else None, vf=raw(mesh.vf) if mesh.vf.size else None)
     for g in shards:
+        g.set_option(4, align)                                      # MAS_OPT_ALIGN_CUTS: both exchange protocols
         g.m_positions, g.m_edges, g.m_faces, g.m_neighbours = d["pos"], d["edges"], d["faces"], (d["st"], d["ix"])
         g.AllocatePrecoditioner(mesh.nv, mesh.ne, mesh.nf)
         g.PreparePreconditioner(d["diag"], d["off"], d["st"], d["ef"], d["ee"], d["vf"], mesh.ef_total, mesh.ee_total, mesh.vf_total,
@@ -63,7 +65,9 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
         assert np.array_equal(g.going_next(), single.going_next())
         assert np.array_equal(g.level_size(), single.level_size())
     # both exchange protocols are exercised: level-2 residuals when every cut falls between level-1 banks, else level 1
-    assert all(g.aligned_cuts for g in shards) == (name in ("cloth_rect512x256", "cloth256")), [g.aligned_cuts for g in shards]
+    aligned = [g.aligned_cuts for g in shards]
+    assert len(set(aligned)) == 1                      # every rank takes the same decision
+    assert aligned[0] == bool(align), (name, aligned)  # these meshes all have an aligned bank within reach of every cut
 
     zs = [torch.full_like(r, float("nan")) for _ in shards]
     for g in shards:
@@ -89,8 +93,9 @@ def test_shards_in_one_process_match_single_device(name, world, pkg, synth):
     assert rel_l2(merged.cpu().numpy(), z1.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("align", [1, 0])
 @pytest.mark.parametrize("name,world", [("cloth96_collisions", 2), ("cloth256", 4), ("cloth_rect512x256", 8)])
-def test_peer_memory_exchange_in_one_process(name, world, pkg, synth):
+def test_peer_memory_exchange_in_one_process(name, world, align, pkg, synth):
     """The production exchange (restriction kernel stores into every rank's arena + device-side flags) with all shards
     living in this process on one GPU, each on its own stream so that they really run concurrently and wait for each
     other on the device.  Results must equal the all-reduce protocol bit for bit, and repeat exactly."""
@@ -106,6 +111,7 @@ def test_peer_memory_exchange_in_one_process(name, world, pkg, synth):
              ef=raw(mesh.ef) if mesh.ef.size else None, ee=raw(mesh.ee) if mesh.ee.size else None, vf=raw(mesh.vf) if mesh.vf.size else None)
     torch.cuda.synchronize()
     for g in shards:
+        g.set_option(4, align)
         g.m_positions, g.m_edges, g.m_faces, g.m_neighbours = d["pos"], d["edges"], d["faces"], (d["st"], d["ix"])
         g.AllocatePrecoditioner(mesh.nv, mesh.ne, mesh.nf)
     arenas = [g.peer_local() for g in shards]
