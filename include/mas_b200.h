@@ -78,7 +78,17 @@ enum
 	/* sharded contexts, 1 (default): move every shard cut (by at most 1/8 of a shard) to a fine bank where the running
 	 * level-1 id is a multiple of 32, so that no level-1 bank straddles two shards and the per-apply exchange carries
 	 * level-2 residuals; 0: even split, exchange of level-1 residuals.  Takes effect at the next mas_prepare. */
-	MAS_OPT_ALIGN_CUTS = 4
+	MAS_OPT_ALIGN_CUTS = 4,
+	/* Q2/Q3 fix mode, default 0 = the reference's literal reading.  1: eeSets and vfSets are read from THEIR
+	 * OWN index 0 (the reference indexes all three arrays by the global stencil index, cpp:357/383, so callers must pad
+	 * them), and the third VF weight is -(1 - b0 - b1) computed from the two stored barycentrics (the reference reads the
+	 * struct's padding float at byte 24 as m_bary[2], cpp:399). */
+	MAS_OPT_STENCIL_FIX = 5,
+	/* Re-sort policy.  0 (default) = the reference as shipped: the Morton order is built by the first
+	 * AllocatePrecoditioner call and never again (m_frameIndex sticks at 1, cpp:44-64, Q1).  N > 0 = the evidently intended
+	 * behaviour "re-run SpaceSort every N frames" (the reference hard-codes 17): every N-th mas_allocate call re-reads the
+	 * positions and adjacency and rebuilds the ordering; sizes must not change. */
+	MAS_OPT_RESORT_PERIOD = 6
 };
 
 /* mas_get_int keys */

@@ -174,6 +174,8 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; break;
+	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
+	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	default: return fail(h, MAS_ERR_INVALID, "unknown option");
 	}
 	drop_graph(h);
@@ -195,8 +197,16 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 	if (!h || numVerts <= 0 || !positions || !nbrStarts) return MAS_ERR_INVALID;
 	Context* c = h;
 	MAS_CUDA(c, cudaSetDevice(c->device));
-	// Q1 (cpp:44-64): m_frameIndex sticks at 1 after the first call, so the reference sorts exactly once per object
-	if (c->allocated) return MAS_OK;
+	// Q1 (cpp:44-64): m_frameIndex sticks at 1 after the first call, so the reference sorts exactly once per object;
+	// MAS_OPT_RESORT_PERIOD > 0 rebuilds the order every that many calls (same sizes)
+	c->allocateCalls += 1;
+	if (c->allocated)
+	{
+		const bool resort = c->optResortPeriod > 0 && (c->allocateCalls - 1) % c->optResortPeriod == 0;
+		if (!resort) return MAS_OK;
+		if (numVerts != c->nv || numEdges != c->ne || numFaces != c->nf) return fail(c, MAS_ERR_INVALID, "re-sort with different sizes");
+		drop_graph(c);
+	}
 	c->nv = numVerts; c->ne = numEdges; c->nf = numFaces;
 	c->nVC = pad32(numVerts);
 	c->numLevel = level_count(numVerts);
@@ -230,7 +240,7 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 	c->ownFineBegin = (int)((long long)nFine * c->rank / c->world);
 	c->ownFineEnd = (int)((long long)nFine * (c->rank + 1) / c->world);
 
-	if (c->world > 1)
+	if (c->world > 1 && !c->arena.p)   // (kept across re-sorts: the peers have it mapped)
 	{
 		// peer-writable arena: two receive buffers for the coarse residuals + control words.  Coarse nodes number about
 		// nv/31 on meshes whose banks stay connected; 1/8 of the vertices (+ slack) is the capacity, checked in mas_prepare.
@@ -269,6 +279,7 @@ int mas_prepare_begin(mas_handle_t h, const float* diagonal, const float* csrOff
 		if (!efSets || !eeSets || !vfSets) return fail(c, MAS_ERR_INVALID, "stencil totals > 0 but a set pointer is null");
 		// Q2: each kind is read at the GLOBAL stencil index, so the caller's arrays span that far (cpp:328/357/383)
 		size_t efBytes = 48 * (size_t)efTotal, eeBytes = 48 * (size_t)(efTotal + eeTotal), vfBytes = 48 * (size_t)total;
+		if (c->optStencilFix) { eeBytes = 48 * (size_t)eeTotal; vfBytes = 48 * (size_t)vfTotal; }
 		if (int rc = stage_in(c, c->efIn, efSets, efBytes, mem, &dEf)) return rc;
 		if (int rc = stage_in(c, c->eeIn, eeSets, eeBytes, mem, &dEe)) return rc;
 		if (int rc = stage_in(c, c->vfIn, vfSets, vfBytes, mem, &dVf)) return rc;

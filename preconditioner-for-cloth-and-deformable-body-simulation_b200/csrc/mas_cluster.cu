@@ -34,21 +34,24 @@ __device__ __forceinline__ int ldi(const unsigned char* p, int off) { return *re
 
 // valid flag per candidate stencil (cpp:330, 359, 385)
 __global__ void stencil_flag_kernel(const unsigned char* __restrict__ ef, const unsigned char* __restrict__ ee,
-	const unsigned char* __restrict__ vf, int efN, int eeN, int total, int* __restrict__ flag)
+	const unsigned char* __restrict__ vf, int efN, int eeN, int total, int fix, int* __restrict__ flag)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
-	const unsigned char* rec = (i < efN ? ef : (i < efN + eeN ? ee : vf)) + 48 * (size_t)i;  // Q2: global index
+	// Q2: the reference reads every kind at the GLOBAL stencil index; MAS_OPT_STENCIL_FIX reads each array from its own zero
+	const int local = i < efN ? i : (fix ? (i < efN + eeN ? i - efN : i - efN - eeN) : i);
+	const unsigned char* rec = (i < efN ? ef : (i < efN + eeN ? ee : vf)) + 48 * (size_t)local;
 	flag[i] = (ldi(rec, 0) >= 0 && ldi(rec, 4) >= 0) ? 1 : 0;
 }
 
 __global__ void stencil_build_kernel(const unsigned char* __restrict__ ef, const unsigned char* __restrict__ ee,
-	const unsigned char* __restrict__ vf, int efN, int eeN, int total, const int* __restrict__ flag,
+	const unsigned char* __restrict__ vf, int efN, int eeN, int total, int fix, const int* __restrict__ flag,
 	const int* __restrict__ slot, const int4* __restrict__ edges, const int4* __restrict__ faces,
 	const int* __restrict__ o2s, Stencil* __restrict__ out, int* __restrict__ outIdx)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total || !flag[i]) return;
+	const size_t eeAt = fix ? (size_t)(i - efN) : (size_t)i, vfAt = fix ? (size_t)(i - efN - eeN) : (size_t)i;
 	Stencil s;
 	s.pad_[0] = s.pad_[1] = s.pad_[2] = 0.f;
 	for (int k = 0; k < 5; ++k) { s.index[k] = 0; s.weight[k] = 0.f; }
@@ -67,7 +70,7 @@ __global__ void stencil_build_kernel(const unsigned char* __restrict__ ef, const
 	}
 	else if (i < efN + eeN)
 	{
-		const unsigned char* p = ee + 48 * (size_t)i;  // EeSet: eId0@0 eId1@4 stiff@8 bary@16 normal@32
+		const unsigned char* p = ee + 48 * eeAt;  // EeSet: eId0@0 eId1@4 stiff@8 bary@16 normal@32
 		int4 e0 = edges[ldi(p, 0)], e1 = edges[ldi(p, 4)];
 		float b0 = ldf(p, 16), b1 = ldf(p, 20);
 		s.n = 4; s.nFirst = 2;
@@ -79,9 +82,10 @@ __global__ void stencil_build_kernel(const unsigned char* __restrict__ ef, const
 	}
 	else
 	{
-		const unsigned char* p = vf + 48 * (size_t)i;  // VfSet: vId@0 fId@4 stiff@8 bary@16, Q3: m_bary[2] is the float at byte 24
+		const unsigned char* p = vf + 48 * vfAt;  // VfSet: vId@0 fId@4 stiff@8 bary@16, Q3: m_bary[2] is the float at byte 24
 		int4 f = faces[ldi(p, 4)];
-		float b0 = ldf(p, 16), b1 = ldf(p, 20), b2 = ldf(p, 24);
+		// fix mode: the third weight is -(1 - b0 - b1), what the padding float stands in for in the literal reading
+		float b0 = ldf(p, 16), b1 = ldf(p, 20), b2 = fix ? __fadd_rn(b0, b1) : ldf(p, 24);
 		s.n = 4; s.nFirst = 3;
 		s.index[0] = f.x; s.index[1] = f.y; s.index[2] = f.z; s.index[3] = ldi(p, 0);
 		s.weight[0] = -b0;
@@ -89,7 +93,7 @@ __global__ void stencil_build_kernel(const unsigned char* __restrict__ ef, const
 		s.weight[2] = -__fsub_rn(1.f, b2);
 		s.weight[3] = 1.f;  // cpp:397-400
 	}
-	const unsigned char* rec = (i < efN ? ef : (i < efN + eeN ? ee : vf)) + 48 * (size_t)i;
+	const unsigned char* rec = i < efN ? ef + 48 * (size_t)i : (i < efN + eeN ? ee + 48 * eeAt : vf + 48 * vfAt);
 	s.stiff = ldf(rec, 8);
 	for (int k = 0; k < 4; ++k) s.dir[k] = ldf(rec, 32 + 4 * k);
 	int dst = slot[i];
@@ -345,7 +349,7 @@ int build_stencils(Context* c, const void* ef, const void* ee, const void* vf, u
 	if (int rc = reserve(c, c->stencilSlot, (size_t)n)) return rc;
 	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
 	stencil_flag_kernel<<<cdiv(n, threads), threads, 0, s>>>((const unsigned char*)ef, (const unsigned char*)ee,
-		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->stencilFlag.p);
+		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->optStencilFix, c->stencilFlag.p);
 	exclusive_scan_kernel<<<1, kScanThreads, 0, s>>>(c->stencilFlag.p, n, c->stencilSlot.p, c->scanTotal.p);
 	c->prepareLaunches += 2;
 	int count = 0;
@@ -356,7 +360,7 @@ int build_stencils(Context* c, const void* ef, const void* ee, const void* vf, u
 	if (int rc = reserve(c, c->stencils, (size_t)count)) return rc;
 	if (int rc = reserve(c, c->stencilIdx, (size_t)count * 5)) return rc;
 	stencil_build_kernel<<<cdiv(n, threads), threads, 0, s>>>((const unsigned char*)ef, (const unsigned char*)ee,
-		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->stencilFlag.p, c->stencilSlot.p, c->edges.p, c->faces.p,
+		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->optStencilFix, c->stencilFlag.p, c->stencilSlot.p, c->edges.p, c->faces.p,
 		c->o2s.p, c->stencils.p, c->stencilIdx.p);
 	c->prepareLaunches += 1;
 	MAS_CUDA(c, cudaGetLastError());

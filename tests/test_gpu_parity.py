@@ -263,3 +263,58 @@ def test_errors_are_reported_not_swallowed(gpu_cls, synth, pkg):
     g.setup_from_mesh(mesh)
     with pytest.raises(pkg.MasError):
         g.Preconditioning(np.zeros((mesh.nv, 4), np.float64), synth.residual(mesh.nv))
+
+
+def test_stencil_fix_mode_equals_literal_reading_of_padded_arrays(gpu_cls, synth):
+    """MAS_OPT_STENCIL_FIX: compact eeSets / vfSets read from their own index 0 and the third VF weight formed
+    from b0 + b1 must reproduce the literal Q2/Q3 reading of the padded arrays the synthetic generator writes (every kind at
+    its global index, b0 + b1 stored in the VfSet padding float)."""
+    m = synth.cloth(96, with_topology=True)
+    mesh = synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
+    r = synth.residual(mesh.nv)
+    lit = gpu_cls(0).setup_from_mesh(mesh)
+    z_lit = np.zeros_like(r)
+    lit.Preconditioning(z_lit, r)
+    n_ef, n_ee, n_vf = mesh.ef_total, mesh.ee_total, mesh.vf_total
+    vf = mesh.vf[n_ef + n_ee:].copy()
+    vf["pad"] = -7.0                                            # the fix must not look at the padding float
+    fix = gpu_cls(0)
+    fix.set_option(5, 1)
+    fix.m_positions, fix.m_edges, fix.m_faces = mesh.positions, mesh.edges, mesh.faces
+    fix.m_neighbours = (mesh.nbr_starts, mesh.nbr_idx)
+    fix.AllocatePrecoditioner(mesh.nv, mesh.ne, mesh.nf)
+    fix.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.ef[:n_ef].copy(), mesh.ee[n_ef:n_ef + n_ee].copy(), vf,
+                              n_ef, n_ee, n_vf)
+    assert fix.stencil_num == lit.stencil_num > 0
+    sa, ma = lit.stencils()
+    sb, mb = fix.stencils()
+    assert np.array_equal(ma, mb) and sa.tobytes() == sb.tobytes()
+    z_fix = np.zeros_like(r)
+    fix.Preconditioning(z_fix, r)
+    assert rel_l2(z_fix, z_lit) < 1e-5                          # collision atomics: setup order is not deterministic (Q7)
+
+
+def test_resort_period_rebuilds_the_morton_order(gpu_cls, synth, oracle_lib):
+    """MAS_OPT_RESORT_PERIOD: 0 = the reference as shipped (one sort per object, Q1); N = every N-th
+    AllocatePrecoditioner call rebuilds the order from the current positions."""
+    mesh = synth.cloth(64)
+    moved = synth.cloth(64)
+    moved.positions = mesh.positions[:, [1, 0, 2, 3]].copy()    # swap x and y: a different Morton order, same topology
+    moved.positions[:, 0] *= 0.5
+    r = synth.residual(mesh.nv)
+    g = gpu_cls(0)
+    g.set_option(6, 2)
+    g.setup_from_mesh(mesh)
+    order0 = g.sorted_get_original()
+    g.m_positions = moved.positions
+    g.AllocatePrecoditioner(mesh.nv, 0, 0)                      # call 2: not yet
+    assert np.array_equal(g.sorted_get_original(), order0)
+    g.AllocatePrecoditioner(mesh.nv, 0, 0)                      # call 3: (3 - 1) % 2 == 0 -> re-sort
+    order1 = g.sorted_get_original()
+    assert not np.array_equal(order1, order0)
+    g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts)
+    z = np.zeros_like(r)
+    g.Preconditioning(z, r)
+    o = make_oracle(oracle_lib, moved, "d")
+    assert np.array_equal(order1, o.sorted_get_original())
+    assert rel_l2(z, o.apply(r)) < 1e-4
