@@ -10,8 +10,10 @@
 // One iteration = 4 launches + the apply's own launches, captured once in a CUDA graph and replayed; the stopping test is
 // evaluated on the device (a flag turns the remaining launches of a batch into no-ops), so the host synchronises once per
 // batch of iterations, not once per iteration.
-//   spmv_dot      Ap = A p (warp per 32 rows, lane per 3x3 block, blocks staged through shared memory so every global
-//                 load is coalesced; segmented shuffle scan adds the blocks of a row), partial sums of p.Ap
+//   spmv_dot      Ap = A p, partial sums of p.Ap.  A is converted once per solve to a sliced-ELL layout (32-row slices,
+//                 every (block slot, entry) of a slice is 32 consecutive floats): lane = row, all loads coalesced, nine
+//                 FMAs per eleven loads and no cross-lane traffic (the CSR kernel it replaces staged blocks through
+//                 shared memory and needed a segmented shuffle scan per 32 blocks: 112 us vs 397 MB at 1M vertices)
 //   axpy_rr       alpha = rz / p.Ap;  x += alpha p;  r -= alpha Ap;  partial sums of r.r
 //   (apply)       z = M^-1 r
 //   dot_rz        partial sums of r.z; one thread evaluates the stopping test for this iteration
@@ -26,6 +28,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPcgThreads = 256;
 constexpr int kPcgWarps = kPcgThreads / 32;
 constexpr int kMaxPartials = 1024;  // CTAs per reduction pass (grid-stride beyond that)
+constexpr int kSpmvBatch = 4;       // block slots whose loads are in flight together in the SpMV
+constexpr int kVecUnroll = 4;       // elements per thread and trip of the vector kernels, loads in flight together
 
 // Scalars: [0] rz  [1] pAp (unused, kept in partials)  [2] rr  [3] rr0  [4] rzNew
 struct PcgState
@@ -55,81 +59,96 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
 	return block_sum(v, sh);
 }
 
-// Ap = A p and partial p.Ap.  One warp per 32 consecutive rows.
-__global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __restrict__ diag, const float* __restrict__ off,
-	const int* __restrict__ ranges, const int* __restrict__ idx, const float4* __restrict__ p, float4* __restrict__ Ap, int nv,
-	double* __restrict__ partials, const volatile PcgState* st)
+// ---- sliced-ELL copy of the caller's block CSR (once per solve) ---------------------------------------------------------
+// slice g = rows 32g .. 32g+31, width w_g = its longest row; slot (g, k, lane) holds the k-th block of row 32g+lane:
+//   ellIdx[sliceStart[g] + 32 k + lane]                (column vertex, -1 = padding)
+//   ellVal[9 (sliceStart[g] + 32 k) + 32 e + lane]     (entry e of the column-major 3x3 block)
+__global__ void ell_width_kernel(const int* __restrict__ ranges, int nv, int* __restrict__ sliceSlots)
 {
-	__shared__ float stage[kPcgWarps][288];
-	__shared__ float acc[kPcgWarps][32][3];
+	const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (g * 32 >= nv) return;
+	const int row = g * 32 + lane;
+	int deg = row < nv ? ranges[row + 1] - ranges[row] : 0;
+	for (int off = 16; off > 0; off >>= 1) deg = max(deg, __shfl_xor_sync(kFull, deg, off));
+	if (lane == 0) sliceSlots[g] = 32 * deg;
+}
+
+__global__ void ell_fill_kernel(const float* __restrict__ off, const int* __restrict__ ranges, const int* __restrict__ idx, int nv,
+	const int* __restrict__ sliceStart, const int* __restrict__ sliceSlots, int* __restrict__ ellIdx, float* __restrict__ ellVal)
+{
+	const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (g * 32 >= nv) return;
+	const int row = g * 32 + lane;
+	const int rs = row < nv ? ranges[row] : 0, re = row < nv ? ranges[row + 1] : 0;
+	const int base = sliceStart[g], width = sliceSlots[g] >> 5;
+	for (int k = 0; k < width; ++k)
+	{
+		const bool has = rs + k < re;
+		ellIdx[base + 32 * k + lane] = has ? idx[rs + k] : -1;
+		const float* m = off + 9 * (size_t)(rs + k);
+		float* dst = ellVal + 9 * (size_t)(base + 32 * k) + lane;
+#pragma unroll
+		for (int e = 0; e < 9; ++e) dst[32 * e] = has ? m[e] : 0.0f;
+	}
+}
+
+// Ap = A p and partial p.Ap.  One warp per 32-row slice, lane = row.
+__global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __restrict__ diag, const int* __restrict__ sliceStart,
+	const int* __restrict__ sliceSlots, const int* __restrict__ ellIdx, const float* __restrict__ ellVal, const float4* __restrict__ p,
+	float4* __restrict__ Ap, int nv, double* __restrict__ partials, const volatile PcgState* st)
+{
 	__shared__ double sh[kPcgWarps];
 	if (st->done) return;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int nWarpRows = (nv + 31) >> 5;
+	const int nSlices = (nv + 31) >> 5;
 	double dot = 0.0;
-	for (int wr = blockIdx.x * kPcgWarps + warp; wr < nWarpRows; wr += gridDim.x * kPcgWarps)
+	for (int g = blockIdx.x * kPcgWarps + warp; g < nSlices; g += gridDim.x * kPcgWarps)
 	{
-		const int r0 = wr * 32, row = r0 + lane;
-		const int rs = ranges[row < nv ? row : nv];   // start of my row (lanes past the end see the total)
-		const int s = __shfl_sync(kFull, rs, 0);
-		const int e = ranges[(r0 + 32) < nv ? (r0 + 32) : nv];
-		acc[warp][lane][0] = acc[warp][lane][1] = acc[warp][lane][2] = 0.f;
-		__syncwarp();
-		for (int c = s; c < e; c += 32)
-		{
-			const int nb = min(32, e - c);
-			// stage 32 blocks (288 floats) with coalesced loads
-			const float* src = off + 9 * (size_t)c;
-			for (int q = lane; q < 9 * nb; q += 32) stage[warp][q] = src[q];
-			__syncwarp();
-			const int blk = c + lane;
-			const bool valid = lane < nb;
-			float cx = 0.f, cy = 0.f, cz = 0.f;
-			int key = -1;
-			if (valid)
-			{
-				const float* m = &stage[warp][9 * lane];   // column-major: m[3j+i] = (i,j)
-				const float4 xv = p[idx[blk]];
-				cx = fmaf(m[0], xv.x, fmaf(m[3], xv.y, m[6] * xv.z));
-				cy = fmaf(m[1], xv.x, fmaf(m[4], xv.y, m[7] * xv.z));
-				cz = fmaf(m[2], xv.x, fmaf(m[5], xv.y, m[8] * xv.z));
-			}
-			// row of my block: the last lane l with rs_l <= blk (binary search over the warp's row starts)
-			{
-				int lo = 0, hi = 31;
-				for (int it = 0; it < 5; ++it)
-				{
-					const int mid = (lo + hi + 1) >> 1;
-					const int v = __shfl_sync(kFull, rs, mid);
-					if (v <= blk) lo = mid; else hi = mid - 1;
-				}
-				if (valid) key = lo;
-			}
-			// segmented inclusive scan over lanes with equal key (contiguous), fixed order
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const float ux = __shfl_up_sync(kFull, cx, o), uy = __shfl_up_sync(kFull, cy, o), uz = __shfl_up_sync(kFull, cz, o);
-				const int uk = __shfl_up_sync(kFull, key, o);
-				if (lane >= o && uk == key) { cx += ux; cy += uy; cz += uz; }
-			}
-			const int nk = __shfl_down_sync(kFull, key, 1);
-			if (valid && (lane == 31 || nk != key))
-			{
-				acc[warp][key][0] += cx; acc[warp][key][1] += cy; acc[warp][key][2] += cz;
-			}
-			__syncwarp();
-		}
+		const int row = g * 32 + lane;
+		const int base = sliceStart[g], width = sliceSlots[g] >> 5;
+		float yx = 0.f, yy = 0.f, yz = 0.f;
+		float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
 		if (row < nv)
 		{
 			const float* d = diag + 9 * (size_t)row;
-			const float4 xv = p[row];
-			const float yx = fmaf(d[0], xv.x, fmaf(d[3], xv.y, fmaf(d[6], xv.z, acc[warp][lane][0])));
-			const float yy = fmaf(d[1], xv.x, fmaf(d[4], xv.y, fmaf(d[7], xv.z, acc[warp][lane][1])));
-			const float yz = fmaf(d[2], xv.x, fmaf(d[5], xv.y, fmaf(d[8], xv.z, acc[warp][lane][2])));
+			xv = p[row];
+			yx = fmaf(d[0], xv.x, fmaf(d[3], xv.y, d[6] * xv.z));
+			yy = fmaf(d[1], xv.x, fmaf(d[4], xv.y, d[7] * xv.z));
+			yz = fmaf(d[2], xv.x, fmaf(d[5], xv.y, d[8] * xv.z));
+		}
+		// Branch-free and in batches of kSpmvBatch slots: first every load of the batch (column indices and blocks, then the
+		// gathers of p), then the FMAs.  Padding slots carry zero blocks and read p[0].  With a branch on the column index
+		// every slot cost two dependent memory round trips and the kernel ran at 3.6 TB/s.
+		for (int k0 = 0; k0 < width; k0 += kSpmvBatch)
+		{
+			int c[kSpmvBatch];
+			float v[kSpmvBatch][9];
+			float4 q[kSpmvBatch];
+#pragma unroll
+			for (int u = 0; u < kSpmvBatch; ++u)
+			{
+				const bool in = k0 + u < width;
+				const int slot = base + 32 * (in ? k0 + u : k0);
+				c[u] = in ? ellIdx[slot + lane] : -1;
+				const float* m = ellVal + 9 * (size_t)slot + lane;
+#pragma unroll
+				for (int e = 0; e < 9; ++e) v[u][e] = in ? m[32 * e] : 0.0f;
+			}
+#pragma unroll
+			for (int u = 0; u < kSpmvBatch; ++u) q[u] = p[c[u] < 0 ? 0 : c[u]];
+#pragma unroll
+			for (int u = 0; u < kSpmvBatch; ++u)
+			{
+				yx = fmaf(v[u][0], q[u].x, fmaf(v[u][3], q[u].y, fmaf(v[u][6], q[u].z, yx)));
+				yy = fmaf(v[u][1], q[u].x, fmaf(v[u][4], q[u].y, fmaf(v[u][7], q[u].z, yy)));
+				yz = fmaf(v[u][2], q[u].x, fmaf(v[u][5], q[u].y, fmaf(v[u][8], q[u].z, yz)));
+			}
+		}
+		if (row < nv)
+		{
 			Ap[row] = make_float4(yx, yy, yz, 0.f);
 			dot += (double)xv.x * yx + (double)xv.y * yy + (double)xv.z * yz;
 		}
-		__syncwarp();
 	}
 	const double t = block_sum(dot, sh);
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
@@ -144,14 +163,27 @@ __global__ void __launch_bounds__(kPcgThreads) axpy_rr_kernel(float4* __restrict
 	const double pAp = reduce_partials(pApPartials, nPartials, sh);
 	const float alpha = (float)(st->rz / pAp);
 	double rr = 0.0;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+	const int stride = gridDim.x * blockDim.x;
+	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += kVecUnroll * stride)
 	{
-		float4 xv = x[i], rv = r[i];
-		const float4 pv = p[i], av = Ap[i];
-		xv.x = fmaf(alpha, pv.x, xv.x); xv.y = fmaf(alpha, pv.y, xv.y); xv.z = fmaf(alpha, pv.z, xv.z);
-		rv.x = fmaf(-alpha, av.x, rv.x); rv.y = fmaf(-alpha, av.y, rv.y); rv.z = fmaf(-alpha, av.z, rv.z);
-		x[i] = xv; r[i] = rv;
-		rr += (double)rv.x * rv.x + (double)rv.y * rv.y + (double)rv.z * rv.z;
+		// all loads of the kVecUnroll elements are issued before the first use (one memory round trip, not four)
+		float4 xv[kVecUnroll], rv[kVecUnroll], pv[kVecUnroll], av[kVecUnroll];
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i < nv) { xv[u] = x[i]; rv[u] = r[i]; pv[u] = p[i]; av[u] = Ap[i]; }
+		}
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i >= nv) break;
+			xv[u].x = fmaf(alpha, pv[u].x, xv[u].x); xv[u].y = fmaf(alpha, pv[u].y, xv[u].y); xv[u].z = fmaf(alpha, pv[u].z, xv[u].z);
+			rv[u].x = fmaf(-alpha, av[u].x, rv[u].x); rv[u].y = fmaf(-alpha, av[u].y, rv[u].y); rv[u].z = fmaf(-alpha, av[u].z, rv[u].z);
+			x[i] = xv[u]; r[i] = rv[u];
+			rr += (double)rv[u].x * rv[u].x + (double)rv[u].y * rv[u].y + (double)rv[u].z * rv[u].z;
+		}
 	}
 	const double t = block_sum(rr, sh);
 	if (threadIdx.x == 0) rrPartials[blockIdx.x] = t;
@@ -164,10 +196,22 @@ __global__ void __launch_bounds__(kPcgThreads) dot_kernel(const float4* __restri
 	__shared__ double sh[kPcgWarps];
 	if (st->done) return;
 	double v = 0.0;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+	const int stride = gridDim.x * blockDim.x;
+	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += kVecUnroll * stride)
 	{
-		const float4 av = a[i], bv = b[i];
-		v += (double)av.x * bv.x + (double)av.y * bv.y + (double)av.z * bv.z;
+		float4 av[kVecUnroll], bv[kVecUnroll];
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i < nv) { av[u] = a[i]; bv[u] = b[i]; }
+		}
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			if (i0 + u * stride >= nv) break;
+			v += (double)av[u].x * bv[u].x + (double)av[u].y * bv[u].y + (double)av[u].z * bv[u].z;
+		}
 	}
 	const double t = block_sum(v, sh);
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
@@ -187,12 +231,25 @@ __global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restric
 	const double rr = reduce_partials(rrPartials, nPartials, sh);
 	const double rzOld = st->rz;
 	const float beta = mode == 0 ? 0.f : (float)(rzNew / rzOld);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x)
+	const int stride = gridDim.x * blockDim.x;
+	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += kVecUnroll * stride)
 	{
-		const float4 zv = z[i];
-		float4 pv = mode == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : p[i];
-		pv.x = fmaf(beta, pv.x, zv.x); pv.y = fmaf(beta, pv.y, zv.y); pv.z = fmaf(beta, pv.z, zv.z); pv.w = 0.f;
-		p[i] = pv;
+		float4 zv[kVecUnroll], pv[kVecUnroll];
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i < nv) { zv[u] = z[i]; pv[u] = mode == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : p[i]; }
+		}
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i >= nv) break;
+			pv[u].x = fmaf(beta, pv[u].x, zv[u].x); pv[u].y = fmaf(beta, pv[u].y, zv[u].y); pv[u].z = fmaf(beta, pv[u].z, zv[u].z);
+			pv[u].w = 0.f;
+			p[i] = pv[u];
+		}
 	}
 	// grid-wide agreement: the state is rewritten by the LAST CTA to finish reading it
 	__shared__ bool last;
@@ -251,6 +308,21 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	const int nPart = grid > gridSpmv ? grid : gridSpmv;
 	const double tol2 = (double)relTol * (double)relTol;
 
+	// sliced-ELL copy of A (see ell_fill_kernel): two small passes, a scan and one pass over the blocks
+	const int nSlices = cdiv(nv, 32);
+	if (int rc = reserve(c, c->pcgSliceSlots, (size_t)nSlices)) return rc;
+	if (int rc = reserve(c, c->pcgSliceStart, (size_t)nSlices)) return rc;
+	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
+	ell_width_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(ranges, nv, c->pcgSliceSlots.p);
+	if (int rc = launch_exclusive_scan(c, c->pcgSliceSlots.p, nSlices, c->pcgSliceStart.p, c->scanTotal.p)) return rc;
+	int totalSlots = 0;
+	MAS_CUDA(c, cudaMemcpyAsync(&totalSlots, c->scanTotal.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	MAS_CUDA(c, cudaStreamSynchronize(st));
+	if (int rc = reserve(c, c->pcgEllIdx, (size_t)(totalSlots > 0 ? totalSlots : 1))) return rc;
+	if (int rc = reserve(c, c->pcgEllVal, (size_t)(totalSlots > 0 ? totalSlots : 1) * 9)) return rc;
+	ell_fill_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(off, ranges, idx, nv, c->pcgSliceStart.p, c->pcgSliceSlots.p,
+		c->pcgEllIdx.p, c->pcgEllVal.p);
+
 	MAS_CUDA(c, cudaMemsetAsync(state, 0, sizeof(PcgState), st));
 	MAS_CUDA(c, cudaMemsetAsync(pA, 0, sizeof(double) * 3 * kMaxPartials, st));
 	copy_b_kernel<<<cdiv(nv, 256), 256, 0, st>>>(b, r, x, nv);
@@ -277,7 +349,8 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
 	if (rc == MAS_OK)
 	{
-		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(diag, off, ranges, idx, p, Ap, nv, pA, state);
+		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(diag, c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
+			nv, pA, state);
 		axpy_rr_kernel<<<grid, kPcgThreads, 0, cap>>>(x, r, p, Ap, nv, pA, nPart, pRR, state);
 		c->applyLaunches = 0;
 		if (usePrecond) rc = apply_forked(c, r, z, cap);   // coarse chain concurrent with the head of the fine solve
