@@ -228,6 +228,8 @@ def run_ours(args):
         if weak:
             workload = (f"cloth {1024 * a}x{1024 * b} ({mesh.nv:,} verts = {world} x 1,048,576), 8-neighbour springs, "
                         f"Morton-sharded over {world} GPUs")
+    elif args.config == 4:
+        mesh = S.cloth_rect_device(2048, 2048, torch.device(dev))      # strong scaling: the 4.2M-vertex cloth split N ways
     else:
         mesh = S.config(args.config)
     nv = mesh.nv

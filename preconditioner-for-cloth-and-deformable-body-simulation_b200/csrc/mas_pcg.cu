@@ -92,6 +92,25 @@ __global__ void ell_fill_kernel(const float* __restrict__ off, const int* __rest
 	}
 }
 
+// two arrays of partial sums at once (one pair of barriers instead of two)
+__device__ __forceinline__ void reduce_partials2(const double* __restrict__ pa, const double* __restrict__ pb, int n, double* sh,
+	double& ra, double& rb)
+{
+	double a = 0.0, b = 0.0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) { a += pa[i]; b += pb[i]; }
+	for (int off = 16; off > 0; off >>= 1)
+	{
+		a += __shfl_xor_sync(kFull, a, off);
+		b += __shfl_xor_sync(kFull, b, off);
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	__syncthreads();
+	if (lane == 0) { sh[warp] = a; sh[nw + warp] = b; }
+	__syncthreads();
+	ra = 0.0; rb = 0.0;
+	for (int w = 0; w < nw; ++w) { ra += sh[w]; rb += sh[nw + w]; }  // every thread, same order
+}
+
 // Ap = A p and partial p.Ap.  One warp per 32-row slice, lane = row.
 __global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __restrict__ diag, const int* __restrict__ sliceStart,
 	const int* __restrict__ sliceSlots, const int* __restrict__ ellIdx, const float* __restrict__ ellVal, const float4* __restrict__ p,
@@ -224,11 +243,11 @@ __global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restric
 	const double* __restrict__ rzPartials, const double* __restrict__ rrPartials, int nPartials, double tol2, int mode,
 	PcgState* stw)
 {
-	__shared__ double sh[kPcgWarps];
+	__shared__ double sh[2 * kPcgWarps];
 	volatile PcgState* st = stw;
 	if (st->done) return;
-	const double rzNew = reduce_partials(rzPartials, nPartials, sh);
-	const double rr = reduce_partials(rrPartials, nPartials, sh);
+	double rzNew, rr;
+	reduce_partials2(rzPartials, rrPartials, nPartials, sh, rzNew, rr);
 	const double rzOld = st->rz;
 	const float beta = mode == 0 ? 0.f : (float)(rzNew / rzOld);
 	const int stride = gridDim.x * blockDim.x;
