@@ -312,6 +312,45 @@ def tet_cube(nx: int, ny: int, nz: int, k: float = 1000.0, m: float = 1.0,
     return Mesh(f"tet{nx}x{ny}x{nz}", nv, positions, starts, idx, diag, off)
 
 
+def from_edges(positions_xyz: np.ndarray, a: np.ndarray, b: np.ndarray, k: float = 1000.0, m: float = 1.0,
+               name: str = "custom") -> Mesh:
+    """A mass-spring mesh over arbitrary undirected edges (a[i], b[i]) in insertion order (both directions pushed, as in
+    the cloth recipe); vertices may have no edges at all.  Edge-case meshes for the parity tests."""
+    nv = int(positions_xyz.shape[0])
+    positions = np.zeros((nv, 4), np.float32)
+    positions[:, :3] = np.asarray(positions_xyz, np.float32)[:, :3]
+    a = np.asarray(a, np.int64).reshape(-1)
+    b = np.asarray(b, np.int64).reshape(-1)
+    starts, idx, src = _csr_from_edge_sequence(nv, a, b)
+    if idx.shape[0]:
+        diag, off = _spring_hessian(positions, starts, idx, src, k, m)
+    else:
+        diag = np.tile((np.float32(m) * np.eye(3, dtype=np.float32)).T.reshape(1, 9), (nv, 1)).astype(np.float32)
+        off = np.zeros((0, 9), np.float32)
+    return Mesh(name, nv, positions, starts, idx, diag, off)
+
+
+def chain(n: int, spacing: float = 0.01) -> Mesh:
+    """n vertices on a slightly bent line, consecutive ones connected (n = 1: a single free vertex)."""
+    t = np.arange(n, dtype=np.float32)
+    pos = np.stack([np.float32(spacing) * t, np.float32(0.3 * spacing) * np.sin(t), np.float32(0.2 * spacing) * np.cos(2 * t)], 1)
+    v = np.arange(max(n - 1, 0), dtype=np.int64)
+    return from_edges(pos, v, v + 1, name=f"chain{n}")
+
+
+def cloth_with_isolated_vertices(n: int = 20, extra: int = 7) -> Mesh:
+    """An n x n cloth plus `extra` vertices without any edge, dropped into the sheet's bounding box (they sort into the
+    cloth's banks and must come out as one-vertex clusters)."""
+    base = cloth(n)
+    rng = np.random.RandomState(5)
+    lo, hi = base.positions[:, :3].min(0), base.positions[:, :3].max(0)
+    iso = rng.uniform(0.1, 0.9, size=(extra, 3)).astype(np.float32) * (hi - lo) + lo
+    pos = np.concatenate([base.positions[:, :3], iso], 0)
+    src = np.repeat(np.arange(base.nv), np.diff(base.nbr_starts))
+    keep = src < base.nbr_idx                       # every undirected edge once, in first-appearance order
+    return from_edges(pos, src[keep], base.nbr_idx[keep], name=f"cloth{n}+iso{extra}")
+
+
 def residual(nv: int, seed: int = 1) -> np.ndarray:
     """r ~ U(-1,1) per component, MT19937(seed), xyz per vertex in order; w = 0."""
     rng = np.random.RandomState(seed)

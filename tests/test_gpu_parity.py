@@ -28,11 +28,17 @@ def _cases(synth):
         "tet16x16x8": lambda: synth.tet_cube(16, 16, 8),
         "cloth200_stiff": lambda: synth.cloth(200, k=1e5),        # ill-conditioned blocks
         "cloth_rect96x40": lambda: synth.cloth_rect(96, 40),      # per-axis Morton normalisation on a non-square sheet
+        "cloth20_isolated_vertices": lambda: synth.cloth_with_isolated_vertices(20, 7),
+        "chain1_single_vertex": lambda: synth.chain(1),           # no edges at all
+        "chain32_exactly_one_bank": lambda: synth.chain(32),
+        "chain33_one_over": lambda: synth.chain(33),
+        "chain100_fragmented_banks": lambda: synth.chain(100),    # bent line: many components per Morton bank
     }
 
 
 CASE_NAMES = ["cloth64", "cloth50_ragged", "cloth7_tiny", "cloth5_single_bank", "cloth64_skew", "cloth96_collisions",
-              "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff", "cloth_rect96x40"]
+              "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff", "cloth_rect96x40", "cloth20_isolated_vertices",
+              "chain1_single_vertex", "chain32_exactly_one_bank", "chain33_one_over", "chain100_fragmented_banks"]
 
 
 @pytest.fixture(scope="module")

@@ -47,6 +47,14 @@ CASES = {
     "cloth64_dense_collisions": lambda s: s.add_collisions(s.cloth(64, with_topology=True), 1024, 1024, 2048, seed=11),
     "tet16x16x8": lambda s: s.tet_cube(16, 16, 8),
     "cloth128_stiff": lambda s: s.cloth(128, k=1e5),
+    "cloth_rect96x40": lambda s: s.cloth_rect(96, 40),          # per-axis Morton normalisation on a non-square sheet
+    "cloth20_isolated_vertices": lambda s: s.cloth_with_isolated_vertices(20, 7),
+    "chain1_single_vertex": lambda s: s.chain(1),               # no edges at all
+    "chain32_exactly_one_bank": lambda s: s.chain(32),
+    # chain(33) / chain(100) (fragmented banks on a tiny mesh) are NOT run through the compiled reference: its fixed-size
+    # allocation (pad32(nv)/32 * 1.5 nodes per level, cpp:112-135, Q6) is overrun by their level-1 counts and it corrupts the
+    # heap (observed: intermittent segfault).  tests/test_gpu_parity.py runs them against the oracle, whose buffers follow
+    # the actual counts.
 }
 
 
