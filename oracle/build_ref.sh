@@ -4,7 +4,8 @@
 # (SeSchwarzPreconditioner.cpp + SeOmp.cpp, read from where they lie under
 # $MAS_REFERENCE_DIR, default /root/reference) into oracle/_ref/:
 #   libmas_ref.so        the reference as shipped
-#   libmas_ref_q5fix.so  same, with the four-line cull at cpp:991-994 removed
+#   libmas_prev.so       SeSchwarzPreconditionerPreviousVersion.h (the older variant), z only
+#   libmas_ref_q5fix.so  same as libmas_ref.so, with the four-line cull at cpp:991-994 removed
 #                        (PrefixSumLx truncates its cross-block
 #                        prefix once a level has >33,792 nodes; needed for the
 #                        4.2M-vertex config only)
@@ -35,7 +36,7 @@ sed -i '/#pragma intrinsic(_BitScanForward)/d' "$tmp/SeIntrinsic.h"
 mkdir -p "$tmp/shim"
 : > "$tmp/shim/intrin.h"
 cp "$here/ref_shim/msvc_shim.h" "$tmp/shim/"
-cp "$here/ref_harness.cpp" "$tmp/"
+cp "$here/ref_harness.cpp" "$here/prev_harness.cpp" "$tmp/"
 
 flags=(-std=c++20 -O2 -DNDEBUG -fopenmp -mavx2 -mfma -mlzcnt -mpopcnt -fpermissive -w -DWIN32 -fPIC
 	-I"$tmp/shim" -I"$tmp" -include msvc_shim.h)
@@ -55,4 +56,6 @@ open(sys.argv[2], "w", encoding="latin-1").write(new)
 EOF
 g++ "${flags[@]}" -shared -o "$out/libmas_ref_q5fix.so" \
 	"$tmp/SeSchwarzPreconditioner_q5.cpp" "$tmp/SeOmp.cpp" "$tmp/ref_harness.cpp"
-echo "built $out/libmas_ref.so $out/libmas_ref_q5fix.so"
+# the older variant (header-only class SeSchwarzPreconditionerPreviousVersion) as a second cross-check of z
+g++ "${flags[@]}" -shared -o "$out/libmas_prev.so" "$tmp/SeOmp.cpp" "$tmp/prev_harness.cpp"
+echo "built $out/libmas_ref.so $out/libmas_ref_q5fix.so $out/libmas_prev.so"

@@ -324,3 +324,29 @@ def test_resort_period_rebuilds_the_morton_order(gpu_cls, synth, oracle_lib):
     o = make_oracle(oracle_lib, moved, "d")
     assert np.array_equal(order1, o.sorted_get_original())
     assert rel_l2(z, o.apply(r)) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["cloth64", "cloth96_stiff", "tet16x16x8"])
+def test_gpu_against_the_previous_version_oracle(name, gpu_cls, synth, oracle_lib):
+    """Second, independent oracle: the reference's OLDER class (oracle/_ref/libmas_prev.so).  The GPU z must be as close to
+    it as the two reference versions' own distances from FP64 arithmetic allow."""
+    from oracle import prev_binding as pb
+    from oracle import ref_binding as rb
+    if not (pb.available() and rb.available()):
+        pytest.skip("oracle/_ref not built")
+    mesh = {"cloth64": lambda: synth.cloth(64), "cloth96_stiff": lambda: synth.cloth(96, k=1e5),
+            "tet16x16x8": lambda: synth.tet_cube(16, 16, 8)}[name]()
+    r = synth.residual(mesh.nv)
+    g = gpu_cls(0).setup_from_mesh(mesh)
+    z = np.zeros_like(r)
+    g.Preconditioning(z, r)
+    prev = pb.PrevPreconditioner().setup(mesh)
+    cur = rb.RefPreconditioner(threads=1)
+    cur.allocate(mesh)
+    cur.prepare()
+    z64 = make_oracle(oracle_lib, mesh, "d").apply(r)
+    z_prev, z_cur = prev.apply(r), cur.apply(r)
+    assert np.array_equal(g.sorted_get_original(), prev.sorted_get_original())
+    e_prev, e_cur, e_gpu = rel_l2(z_prev, z64), rel_l2(z_cur, z64), rel_l2(z, z64)
+    assert e_gpu <= 2 * max(e_prev, e_cur) + 1e-6, (e_gpu, e_prev, e_cur)
+    assert rel_l2(z, z_prev) <= e_gpu + e_prev + 1e-6

@@ -112,3 +112,30 @@ def test_q5_scan_bug_is_not_reproduced(ref_lib, oracle_lib, synth):
     a, b = make_ref(ref_lib, mesh), make_ref(ref_lib, mesh, q5fix=True)
     assert_structure_equal(a, b, mesh.nv)
     assert_structure_equal(a, make_oracle(oracle_lib, mesh), mesh.nv)
+
+
+PREV_CASES = {"cloth64_soft": lambda s: s.cloth(64, k=10.0), "cloth64": lambda s: s.cloth(64),
+              "cloth96_stiff": lambda s: s.cloth(96, k=1e5), "tet16x16x8": lambda s: s.tet_cube(16, 16, 8)}
+
+
+@pytest.mark.parametrize("name", list(PREV_CASES))
+def test_previous_version_is_a_second_cross_check(name, ref_lib, oracle_lib, synth):
+    """SeSchwarzPreconditionerPreviousVersion.h (the older variant, compiled unmodified into oracle/_ref/libmas_prev.so):
+    same Morton order and cluster count as the current class, and a z that differs from it by rounding only
+    (5e-7 at k/m = 10, 1.5e-5 at 1e3, 1e-2 at 1e5 — on stiff blocks it is the current version that is far
+    from exact arithmetic).  The restatement must sit within the spread of the two reference versions."""
+    from oracle import prev_binding as pb
+    if not pb.available():
+        pytest.skip("oracle/_ref/libmas_prev.so not built (needs /root/reference)")
+    mesh = PREV_CASES[name](synth)
+    cur = make_ref(ref_lib, mesh)
+    prev = pb.PrevPreconditioner().setup(mesh)
+    o32, o64 = make_oracle(oracle_lib, mesh, "f"), make_oracle(oracle_lib, mesh, "d")
+    assert np.array_equal(prev.sorted_get_original(), cur.sorted_get_original())
+    assert prev.total_clusters == cur.total_clusters == o32.total_clusters
+    r = synth.residual(mesh.nv)
+    z_cur, z_prev, z32, z64 = cur.apply(r), prev.apply(r), o32.apply(r), o64.apply(r)
+    e_cur, e_prev = rel_l2(z_cur, z64), rel_l2(z_prev, z64)
+    assert e_prev < 5e-3 and np.all(z_prev[:, 3] == 0)
+    assert rel_l2(z_prev, z_cur) <= e_cur + e_prev + 1e-6
+    assert rel_l2(z32, z_prev) <= 1.5 * (e_cur + e_prev) + 2e-6
