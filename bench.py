@@ -5,8 +5,9 @@
 
 One "step" = one Preconditioning() apply (the per-PCG-iteration hot path, SeSchwarzPreconditioner.cpp:100-110) over
 the whole synthetic mesh.  N>1 is launched by torchrun (one rank per GPU); the 32-node fine domains are sharded in
-Morton-contiguous ranges and the only data-path exchange is one NCCL all-reduce of the coarse-level residuals per
-apply (and one of the coarse Galerkin accumulators per setup).  Scaling (N>1, default config): "weak" (default) shards ONE
+Morton-contiguous ranges and the only data-path exchange per apply is an all-gather of the level-2 residuals over peer
+memory inside the apply graph (NCCL all-reduce with --nccl-exchange), plus one NCCL all-reduce of the coarse Galerkin
+accumulators per setup.  Scaling (N>1, default config): "weak" (default) shards ONE
 cloth of N x 1,048,576 vertices (1024x1024, 2048x1024, 2048x2048, 4096x2048 for N = 1, 2, 4, 8), i.e. per-GPU work is
 fixed at the 1M-vertex cloth the metric is quoted on and `value` counts 1M-vertex applies/s over all ranks
 (N x whole-mesh applies/s); "--scaling strong" keeps the 1M-vertex mesh and splits it N ways (latency-bound from N = 4).

@@ -4,7 +4,8 @@
 //
 // Kernels:
 //   restrict_fine   r (original order) -> level-1 residuals; level 0 is never materialised
-//   restrict_l1     level 1 -> 2;  restrict_top: one CTA walks level 2 -> 3 -> ... (a few thousand nodes)
+//   restrict_l1     level 1 -> 2 (and 2 -> 3 on large meshes);  restrict_top: one CTA walks the top levels
+//   gather_peers    (sharded contexts) publish / wait / pull of the other ranks' coarse residuals over peer memory
 //   solve_coarse    Z_l = inv_l * R_l for every block of levels >= 1, four warps per block (latency-bound)
 //   prolong_sum     per level-1 node: Z_1 + Z_2[parent] + ... (what CollectFinalZ adds to each of its vertices)
 //   solve_fine      gathers r again (L2 resident), multiplies by the packed level-0 inverse, adds the level-1 sum
@@ -21,7 +22,6 @@
 //
 // Every sum is evaluated in a fixed order (no float atomics): results are run-to-run deterministic.
 #include "mas_internal.h"
-#include <cstdlib>
 
 namespace mas {
 

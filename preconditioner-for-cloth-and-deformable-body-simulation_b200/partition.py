@@ -3,17 +3,19 @@
 The reference is single-process (OpenMP only); this layer is new.  What shards and what is exchanged:
 
   * fine domains (97 % of the bytes) are split into `world` contiguous ranges of banks in Morton order; rank g
-    assembles, inverts and applies only its own banks and produces z only for its own vertices;
+    assembles, inverts and applies only its own banks and produces z only for its own vertices.  The CUDA engine moves
+    the cuts (during PreparePreconditioner) to banks where the running level-1 id is a multiple of 32, so that no level-1
+    bank straddles two shards: query `engine.owned_fine_blocks` after the first prepare;
   * level-1 nodes are owned by exactly one fine bank (clustering is per bank, cpp:565-740), so the restriction
-    r -> R_1 is local; every rank then needs the complete coarse residual, which is ONE sum over ranks of the small
-    coarse buffer per apply (0.54 MB at 1M vertices): `exchange(1)`;
+    r -> R_1 is local, and with aligned cuts so are the level-1 solves and the restriction R_1 -> R_2; every rank then
+    needs the complete level-2 residual (nv/1024 nodes): the one exchange per apply, `exchange(1)`;
   * setup has ONE sum over ranks of the coarse Galerkin accumulators (FP64): `exchange(0)`;
-  * levels >= 1 are solved redundantly on every rank (3 % of the blocks), which removes any exchange of z;
+  * levels >= 2 are solved redundantly on every rank, which removes any exchange of z;
   * production path for the apply exchange: `attach_peers()` maps every rank's exchange arena into every other rank
-    (CUDA IPC handles travel over torch.distributed once); from then on the level-0 restriction kernel itself stores
-    the level-1 residuals into all peers over NVLink and raises a flag, the coarse levels wait on the flags on the
-    device, and Preconditioning() is a single graph launch per rank — no NCCL call and no host sync per apply.
-    Without attached peers the exchange is one `all_reduce` between apply_begin and apply_end (the baseline).
+    (CUDA IPC handles travel over torch.distributed once); from then on a kernel inside the apply graph publishes the
+    rank's residuals in its own arena, raises a flag in every peer, waits for the peers' flags on the device and pulls
+    their slices over NVLink: Preconditioning() is a single graph launch per rank — no NCCL call and no host sync per
+    apply.  Without attached peers the exchange is one `all_reduce` between apply_begin and apply_end (the baseline).
 
 `ShardedSchwarzPreconditioner` drives a per-rank engine through begin -> exchange -> end.  The engine is
 `SeSchwarzPreconditioner` (CUDA, exchange buffers are device tensors, NCCL) in production; the CPU tests inject a
@@ -25,7 +27,8 @@ from typing import Optional, Tuple
 
 
 def fine_bank_range(n_fine_banks: int, rank: int, world: int) -> Tuple[int, int]:
-    """[begin, end) of the fine banks rank `rank` owns; identical to mas_allocate's split (csrc/mas_api.cu)."""
+    """[begin, end) of the fine banks rank `rank` owns under the EVEN split (the numpy engine of the CPU tests, and the CUDA
+    engine before its first prepare or with MAS_OPT_ALIGN_CUTS = 0)."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world")
     return n_fine_banks * rank // world, n_fine_banks * (rank + 1) // world
