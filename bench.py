@@ -124,8 +124,11 @@ def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
     """Times the reference's own CPU implementation (oracle/_ref = SeSchwarzPreconditioner.cpp compiled here) or, if
     that shared object did not travel, the plain-C oracle port.  Returns (applies/s, setup_ms, kind)."""
     from oracle import ref_binding as rb
-    if rb.available():
-        p = rb.RefPreconditioner(threads=threads)
+    # beyond 33,792 level-1 nodes (nv > 1,081,344) the stock reference truncates a scan (Q5, cpp:989-994) and then overruns
+    # its own buffers (observed: segfault at 2048^2): such meshes are timed on the build with that four-line cull removed
+    big = mesh.nv > 33792 * 32
+    if rb.available(q5fix=big):
+        p = rb.RefPreconditioner(threads=threads, q5fix=big)
         kind = "reference"
     else:
         from oracle import oracle_binding as ob
@@ -155,8 +158,9 @@ def cpu_reference_pcg(mesh, b, threads: int):
     """PCG to 1e-5 on the host: scipy block-CSR SpMV + the reference's own Preconditioning() (oracle/_ref), all threads."""
     from oracle import ref_binding as rb
     from oracle.cpu_pcg import bsr_matrix, cpu_pcg
-    if rb.available():
-        p = rb.RefPreconditioner(threads=threads)
+    big = mesh.nv > 33792 * 32
+    if rb.available(q5fix=big):
+        p = rb.RefPreconditioner(threads=threads, q5fix=big)
         kind = "reference"
     else:
         from oracle import oracle_binding as ob
