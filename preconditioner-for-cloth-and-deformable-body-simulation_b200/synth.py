@@ -351,6 +351,43 @@ def cloth_with_isolated_vertices(n: int = 20, extra: int = 7) -> Mesh:
     return from_edges(pos, src[keep], base.nbr_idx[keep], name=f"cloth{n}+iso{extra}")
 
 
+def _undirected_edges(mesh: Mesh):
+    """Every undirected edge of `mesh` once, in first-appearance order."""
+    src = np.repeat(np.arange(mesh.nv), np.diff(mesh.nbr_starts))
+    keep = src < mesh.nbr_idx
+    return src[keep].astype(np.int64), mesh.nbr_idx[keep].astype(np.int64)
+
+
+def stacked_cloth(n: int = 24, layers: int = 2, k: float = 1000.0) -> Mesh:
+    """`layers` n x n sheets lying exactly on top of each other (a folded garment at rest): vertex (i,j) of every layer has
+    the same position, hence the same Morton code, so the order inside each group of coincident vertices is decided by the
+    tie rule alone (ascending original index; the reference's std::sort leaves it unspecified, cpp:238-243).  Layers are
+    stitched with springs between (i,j) of one layer and (i+1,j) of the next (never zero length)."""
+    base = cloth(n, k=k)
+    a0, b0 = _undirected_edges(base)
+    nv1 = base.nv
+    pos = np.concatenate([base.positions[:, :3]] * layers, 0)
+    a = [a0 + l * nv1 for l in range(layers)]
+    b = [b0 + l * nv1 for l in range(layers)]
+    v = np.arange(nv1, dtype=np.int64)
+    stitch = v[(v % n) + 1 < n]
+    for l in range(layers - 1):
+        a.append(stitch + l * nv1)
+        b.append(stitch + 1 + (l + 1) * nv1)
+    return from_edges(pos, np.concatenate(a), np.concatenate(b), k=k, name=f"stacked{layers}x{n}")
+
+
+def cloth_with_duplicate_edges(n: int = 24, every: int = 5) -> Mesh:
+    """An n x n cloth whose adjacency lists every `every`-th spring twice (parallel springs / a caller that does not
+    deduplicate): the neighbour lists then hold repeated indices, each with its own off-diagonal block, and the blocks
+    must add up (the reference's += at cpp:1292-1298)."""
+    base = cloth(n)
+    a0, b0 = _undirected_edges(base)
+    dup = np.arange(0, a0.shape[0], every)
+    return from_edges(base.positions[:, :3], np.concatenate([a0, a0[dup]]), np.concatenate([b0, b0[dup]]),
+                      name=f"cloth{n}+dup")
+
+
 def residual(nv: int, seed: int = 1) -> np.ndarray:
     """r ~ U(-1,1) per component, MT19937(seed), xyz per vertex in order; w = 0."""
     rng = np.random.RandomState(seed)

@@ -1,0 +1,72 @@
+"""GPU tests at the edges of the input space that the earlier files do not reach: equal Morton codes (the tie rule),
+repeated neighbour indices, and the largest mesh the five-level hierarchy holds.  Runs last (file name) so that a failure
+here does not mask the parity, PCG and sharded suites under `pytest -x`."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import gpu_cls, test_structure_and_apply_vs_oracle as _structure_and_apply  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["stacked2x24", "stacked3x20", "cloth24_duplicate_edges"])
+def test_ties_and_duplicate_neighbours_vs_oracle(name, gpu_cls, synth, oracle_lib, monkeypatch):
+    """stacked*: coincident sheets = groups of equal Morton codes; the stable radix sort over an iota payload must give the
+    oracle's (code, original index) order, and everything downstream of it bit for bit.  duplicate_edges: neighbour lists
+    with repeated indices, each with its own 3x3 block (they add up, cpp:1292-1298)."""
+    import test_gpu_parity as tp
+    mesh = {"stacked2x24": lambda: synth.stacked_cloth(24, 2), "stacked3x20": lambda: synth.stacked_cloth(20, 3),
+            "cloth24_duplicate_edges": lambda: synth.cloth_with_duplicate_edges(24)}[name]
+    monkeypatch.setattr(tp, "_cases", lambda s: {name: mesh})
+    _structure_and_apply(name, gpu_cls, synth, oracle_lib)
+
+
+def test_one_vertex_over_the_five_level_limit_is_refused(gpu_cls, pkg):
+    """32^5 + 1 vertices need a sixth level, which the Int4 ancestor table (SeSchwarzPreconditioner.h:96) cannot hold: the
+    reference would overrun it; the C ABI returns MAS_ERR_UNSUPPORTED before touching any input."""
+    g = gpu_cls(0)
+    g.m_positions = np.zeros((1, 4), np.float32)
+    g.m_neighbours = (np.zeros(2, np.int32), np.zeros(1, np.int32))
+    with pytest.raises(pkg.MasError, match="more than 5 levels"):
+        g.AllocatePrecoditioner(32 ** 5 + 1, 0, 0)
+
+
+def test_maximum_size_33_million_vertices(gpu_cls, synth):
+    """The largest supported mesh: 8192 x 4096 cloth = 33,554,432 vertices = exactly five full levels, 1,082,401 domains,
+    20.2 GB of packed inverses (64 GB of HBM in use with the caller's Hessian).  Hierarchy sizes are exact; M^-1 is checked
+    through its size-independent properties (tools/max_size_check.py prints the timings: setup 151 ms, apply 3.28 ms)."""
+    import torch
+    dev = torch.device("cuda:0")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~70 GB of free HBM")
+    mesh = synth.cloth_rect_device(8192, 4096, dev)
+    nv = mesh.nv
+    g = gpu_cls(0)
+    g.m_positions, g.m_neighbours = mesh.positions, (mesh.nbr_starts, mesh.nbr_idx)
+    g.AllocatePrecoditioner(nv, 0, 0)
+    g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts)
+    assert g.num_level == 5 and g.num_blocks == 1082401
+    assert g.level_size().tolist() == [[0, 0], [1048576, 33554432], [32768, 34603008], [1024, 34635776], [32, 34636800],
+                                       [1, 34636832]]
+    gen = torch.Generator(device=dev).manual_seed(1)
+    r1 = torch.rand((nv, 4), generator=gen, device=dev) * 2 - 1
+    r2 = torch.rand((nv, 4), generator=gen, device=dev) * 2 - 1
+    r1[:, 3] = 0
+    r2[:, 3] = 0
+    z1, z2, z12, z1b = (torch.empty_like(r1) for _ in range(4))
+    g.Preconditioning(z1, r1)
+    g.Preconditioning(z2, r2)
+    g.Preconditioning(z12, 2.0 * r1 - 0.5 * r2)
+    g.Preconditioning(z1b, r1)
+    torch.cuda.synchronize()
+    d = lambda a, b: float((a[:, :3].double() * b[:, :3].double()).sum())
+    assert bool(torch.isfinite(z1).all()) and bool((z1[:, 3] == 0).all())
+    assert abs(d(r1, z2) - d(r2, z1)) <= 1e-6 * abs(d(r1, z1))
+    assert d(r1, z1) > 0 and d(r2, z2) > 0
+    lin = 2.0 * z1 - 0.5 * z2
+    assert float((z12 - lin)[:, :3].norm() / lin[:, :3].norm()) < 1e-5
+    assert torch.equal(z1, z1b)
+    g.close()
+    del mesh, r1, r2, z1, z2, z12, z1b, lin
+    torch.cuda.empty_cache()

@@ -51,6 +51,7 @@ CASES = {
     "cloth20_isolated_vertices": lambda s: s.cloth_with_isolated_vertices(20, 7),
     "chain1_single_vertex": lambda s: s.chain(1),               # no edges at all
     "chain32_exactly_one_bank": lambda s: s.chain(32),
+    "cloth24_duplicate_edges": lambda s: s.cloth_with_duplicate_edges(24),   # repeated neighbour indices: blocks add up
     # chain(33) / chain(100) (fragmented banks on a tiny mesh) are NOT run through the compiled reference: its fixed-size
     # allocation (pad32(nv)/32 * 1.5 nodes per level, cpp:112-135, Q6) is overrun by their level-1 counts and it corrupts the
     # heap (observed: intermittent segfault).  tests/test_gpu_parity.py runs them against the oracle, whose buffers follow
@@ -81,6 +82,24 @@ def test_oracle_matches_reference(name, ref_lib, oracle_lib, synth):
         assert e_ref < 5e-2
         assert np.all(z_ref[:, 3] == 0) and np.all(z32[:, 3] == 0)
         assert np.abs(ref.mapped_r(tc)[:, :3] - o32.mapped_r()).max() <= 1e-4 * max(1.0, np.abs(o32.mapped_r()).max())
+
+
+@pytest.mark.parametrize("layers,n", [(2, 24), (3, 20)])
+def test_tie_rule_on_coincident_vertices(layers, n, ref_lib, oracle_lib, synth):
+    """Sheets lying exactly on top of each other give groups of EQUAL Morton codes.  The reference sorts with std::sort
+    (cpp:238-243), which leaves the order inside a group unspecified; the restatement (and the CUDA path, a stable radix
+    sort over an iota payload) define it as ascending original index.  Pinned here: the reference computes the same codes
+    and the same sorted code sequence, and the restatement's permutation is the (code, index) lexicographic order."""
+    mesh = synth.stacked_cloth(n, layers)
+    ref, o = make_ref(ref_lib, mesh), make_oracle(oracle_lib, mesh)
+    code = o.morton()
+    assert np.array_equal(code, ref.morton())
+    s2o, s2o_ref = o.sorted_get_original(), ref.sorted_get_original()
+    assert np.array_equal(code[s2o], code[s2o_ref])                       # same keys in the same places
+    assert np.array_equal(np.sort(s2o_ref), np.arange(mesh.nv))
+    assert int((np.diff(code[s2o].astype(np.int64)) == 0).sum()) == (layers - 1) * n * n
+    assert np.array_equal(s2o, np.lexsort((np.arange(mesh.nv), code)).astype(np.int32))
+    assert np.array_equal(o.original_get_sorted()[s2o], np.arange(mesh.nv))
 
 
 def test_known_structure_hashes(ref_lib, oracle_lib, synth):
