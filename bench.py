@@ -15,6 +15,7 @@ fixed at the 1M-vertex cloth the metric is quoted on and `value` counts 1M-verte
 Keys beyond the base contract:
   value          applies/s with r and z resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e            same metric through the public host-pointer API: pinned host r -> H2D -> apply -> D2H z, every step
+                 (timed with both host stagings the library offers, copy engine and MAS_OPT_HOST_PULL; the better is reported)
   setup_ms       PreparePreconditioner() per call, device-resident inputs (CUDA events inside the library)
   roofline       dominant kernel (level-0 solve): algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline   the reference's own CPU code (oracle/_ref, all host threads) on the same mesh; rank 0, N=1 only
@@ -455,6 +456,34 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": int(rank_bytes), "traffic": None,
                 "per_rank_fine_kernel_ms": per_rank_fine_ms,
                 "aligned_cuts": g.aligned_cuts}
+    # ---- e2e with the other host staging (MAS_OPT_HOST_PULL: a kernel pulls the page-locked residual through its device
+    # mapping instead of the copy engine; bit-identical z).  Which one is faster depends on the host (the copy engine reads
+    # host memory at 15-55 GB/s depending on the box, profiles/r01_pcie_staging.json), so both are timed and the better one is
+    # reported, by name.  Runs last and guarded: a failure here leaves every number above untouched.
+    e2e_note = "mas_apply(MAS_MEM_HOST): pinned host r -> H2D -> apply graph -> D2H z, synchronous"
+    e2e_modes = {"copy_engine": e2e_rate}
+    e2e_staging = "copy_engine"
+    if world == 1 and not args.lean:
+        try:
+            z_ce = z_h.clone()
+            g.set_option(7, 1)
+            for _ in range(3):
+                e2e_step()
+            torch.cuda.synchronize()
+            identical = bool(torch.equal(z_h, z_ce))
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            pull_rate = e2e_steps / (time.perf_counter() - t0)
+            g.set_option(7, 0)
+            e2e_modes["host_pull"] = pull_rate
+            e2e_modes["host_pull_bit_identical"] = identical
+            if identical and pull_rate > e2e_rate:
+                e2e_rate, e2e_staging = pull_rate, "host_pull (MAS_OPT_HOST_PULL=1)"
+        except Exception as exc:                      # noqa: BLE001
+            e2e_modes["host_pull_error"] = repr(exc)
+
     out = {
         "metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -472,8 +501,8 @@ def run_ours(args):
         "setup_ms": setup_ms, "setup_device_ms": setup_device_ms,
         "e2e": {"value": units * e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv * world,
                 "d2h_bytes_per_step": 16 * nv * world, "steps": e2e_steps,
-                "note": "every rank copies the whole r in and its z out over its own PCIe link" if world > 1 else
-                        "mas_apply(MAS_MEM_HOST): pinned host r -> H2D -> apply graph -> D2H z, synchronous"},
+                "staging": e2e_staging, "applies_per_s_by_staging": e2e_modes,
+                "note": "every rank copies the whole r in and its z out over its own PCIe link" if world > 1 else e2e_note},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "pcg": pcg,
     }

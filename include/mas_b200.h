@@ -88,7 +88,14 @@ enum
 	 * AllocatePrecoditioner call and never again (m_frameIndex sticks at 1, cpp:44-64, Q1).  N > 0 = the evidently intended
 	 * behaviour "re-run SpaceSort every N frames" (the reference hard-codes 17): every N-th mas_allocate call re-reads the
 	 * positions and adjacency and rebuilds the ordering; sizes must not change. */
-	MAS_OPT_RESORT_PERIOD = 6
+	MAS_OPT_RESORT_PERIOD = 6,
+	/* Host-pointer mas_apply (MAS_MEM_HOST) only.  0 (default): the residual crosses PCIe with cudaMemcpyAsync (copy
+	 * engine).  1: when the caller's residual buffer is page-locked (cudaHostAlloc / cudaHostRegister, detected with
+	 * cudaPointerGetAttributes) a kernel PULLS it through its device mapping with coalesced 16-byte loads instead; pageable
+	 * buffers still take the copy engine.  Measured on a virtualised B200 host whose copy engine reads host memory at
+	 * 15-20 GB/s while SM loads reach 33 GB/s and D2H runs at 56 GB/s either way (tools/pcie_bound.py); z always returns
+	 * through the copy engine.  Results are bit-identical. */
+	MAS_OPT_HOST_PULL = 7
 };
 
 /* mas_get_int keys */

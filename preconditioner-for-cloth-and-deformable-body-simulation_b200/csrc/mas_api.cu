@@ -50,6 +50,36 @@ static int stage_in(Context* c, DevBuf<T>& buf, const void* src, size_t count, i
 	return MAS_OK;
 }
 
+// MAS_OPT_HOST_PULL: the residual of a host-pointer apply read straight out of page-locked host memory (its device mapping)
+// with coalesced 16-byte loads, four independent loads per thread in flight, and stored to the staging buffer in HBM.
+__global__ void __launch_bounds__(256) pull_host_kernel(const float4* __restrict__ mapped, float4* __restrict__ dst, int n)
+{
+	const int stride = gridDim.x * blockDim.x;
+	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride)
+	{
+		float4 v[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (i0 + u * stride < n) v[u] = mapped[i0 + u * stride];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (i0 + u * stride < n) dst[i0 + u * stride] = v[u];
+	}
+}
+
+// device-side address of a page-locked host buffer, or nullptr for pageable memory (which only the copy engine can read)
+static const float4* mapped_host_pointer(const void* host)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, host) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+	return reinterpret_cast<const float4*>(at.devicePointer);
+}
+
 static void drop_graph(Context* c)
 {
 	if (c->applyGraph)
@@ -177,6 +207,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; break;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
+	case MAS_OPT_HOST_PULL: h->optHostPull = value ? 1 : 0; return MAS_OK;   // staging only: the apply graph stays valid
 	default: return fail(h, MAS_ERR_INVALID, "unknown option");
 	}
 	drop_graph(h);
@@ -375,7 +406,16 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
 	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
-	MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, sizeof(float4) * (size_t)c->nv, cudaMemcpyHostToDevice, c->stream));
+	const float4* mapped = c->optHostPull ? mapped_host_pointer(residual) : nullptr;
+	if (mapped)
+	{
+		int grid = cdiv(c->nv, 4 * 256);
+		if (grid > 32 * c->smCount) grid = 32 * c->smCount;
+		pull_host_kernel<<<grid, 256, 0, c->stream>>>(mapped, c->rIn.p, c->nv);
+		MAS_CUDA(c, cudaGetLastError());
+	}
+	else
+		MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, sizeof(float4) * (size_t)c->nv, cudaMemcpyHostToDevice, c->stream));
 	if (int rc = run_apply_device(c, c->rIn.p, c->zOut.p)) return rc;
 	// a shard only produces its own vertices' z; copy everything, the caller merges shards
 	MAS_CUDA(c, cudaMemcpyAsync(z, c->zOut.p, sizeof(float4) * (size_t)c->nv, cudaMemcpyDeviceToHost, c->stream));

@@ -70,3 +70,22 @@ def test_maximum_size_33_million_vertices(gpu_cls, synth):
     g.close()
     del mesh, r1, r2, z1, z2, z12, z1b, lin
     torch.cuda.empty_cache()
+
+
+def test_host_pull_staging_is_bit_identical(gpu_cls, synth):
+    """MAS_OPT_HOST_PULL: a page-locked residual is pulled by a kernel through its device mapping instead of the copy
+    engine; pageable buffers keep the copy engine.  Same z, bit for bit, in every combination."""
+    import torch
+    mesh = synth.cloth(96)
+    g = gpu_cls(0).setup_from_mesh(mesh)
+    r_np = synth.residual(mesh.nv)
+    r_pin = torch.from_numpy(r_np.copy()).pin_memory()
+    z_ce, z_pull = torch.zeros_like(r_pin).pin_memory(), torch.full_like(r_pin, 7.0).pin_memory()
+    g.Preconditioning(z_ce, r_pin)
+    g.set_option(7, 1)
+    g.Preconditioning(z_pull, r_pin)
+    assert torch.equal(z_ce, z_pull)
+    z_pageable = np.full_like(r_np, 3.0)
+    g.Preconditioning(z_pageable, r_np)                   # pageable r: copy engine even with the option on
+    assert np.array_equal(z_pageable, z_ce.numpy())
+    g.set_option(7, 0)
