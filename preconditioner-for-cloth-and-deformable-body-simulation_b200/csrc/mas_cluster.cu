@@ -20,6 +20,8 @@
 //    thread-timing dependent, cpp:407).
 #include "mas_internal.h"
 
+#include <utility>
+
 namespace mas {
 
 namespace {
@@ -382,13 +384,13 @@ static int number_level(Context* c, unsigned* mask, int count, int addSelf, int 
 	// goingNext must hold [0, nextBegin)
 	if ((size_t)nextBegin > c->goingNext.cap)
 	{
-		DevBuf<int> bigger;
+		TempBuf<int> bigger;
 		if (int rc = reserve(c, bigger, (size_t)nextBegin * 2)) return rc;
 		MAS_CUDA(c, cudaMemsetAsync(bigger.p, 0, sizeof(int) * bigger.cap, s));
 		if (c->goingNext.p) MAS_CUDA(c, cudaMemcpyAsync(bigger.p, c->goingNext.p, sizeof(int) * c->goingNext.cap, cudaMemcpyDeviceToDevice, s));
 		MAS_CUDA(c, cudaStreamSynchronize(s));
-		release(c->goingNext);
-		c->goingNext = bigger;
+		std::swap(c->goingNext.p, bigger.p);       // the old array leaves with `bigger`
+		std::swap(c->goingNext.cap, bigger.cap);
 	}
 	number_components_kernel<<<cdiv((long long)nBanks * 32, threads), threads, 0, s>>>(mask, count, c->bankPrefix.p, begin,
 		nextBegin, idOut, c->goingNext.p);

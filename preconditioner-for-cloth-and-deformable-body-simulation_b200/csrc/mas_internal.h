@@ -219,6 +219,16 @@ void release(DevBuf<T>& b)
 	b.cap = 0;
 }
 
+// scratch allocation local to one call: freed on every return path
+template <typename T>
+struct TempBuf : DevBuf<T>
+{
+	TempBuf() = default;
+	TempBuf(const TempBuf&) = delete;
+	TempBuf& operator=(const TempBuf&) = delete;
+	~TempBuf() { release(*this); }
+};
+
 inline int pad32(int x) { return (x + 31) / 32 * 32; }
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -159,7 +159,7 @@ int order_vertices(Context* c, const float4* positions, const int* inStarts, con
 	int nPartials = c->smCount * 4;
 	if (nPartials > cdiv(nv, kReduceThreads)) nPartials = cdiv(nv, kReduceThreads);
 	if (nPartials < 1) nPartials = 1;
-	DevBuf<float4> partials;
+	TempBuf<float4> partials;
 	if (int rc = reserve(c, partials, (size_t)2 * nPartials)) return rc;
 	if (int rc = reserve(c, c->aabb, 8)) return rc;
 	aabb_partial_kernel<<<nPartials, kReduceThreads, 0, s>>>(positions, positions, nv, partials.p, nPartials);
@@ -192,22 +192,19 @@ int order_vertices(Context* c, const float4* positions, const int* inStarts, con
 	remap_adjacency_kernel<<<cdiv(nv, threads), threads, 0, s>>>(c->s2o.p, c->o2s.p, inStarts, inIdx, c->adjStart.p, nv, c->adjIdx.p);
 	MAS_CUDA(c, cudaGetLastError());
 	MAS_CUDA(c, cudaStreamSynchronize(s));
-	release(partials);
 	return MAS_OK;
 }
 
 int morton_encode_points(Context* c, const float* xyz, int count, unsigned long long* out)
 {
-	DevBuf<float> in;
-	DevBuf<unsigned long long> codes;
+	TempBuf<float> in;
+	TempBuf<unsigned long long> codes;
 	if (int rc = reserve(c, in, (size_t)3 * count)) return rc;
 	if (int rc = reserve(c, codes, (size_t)count)) return rc;
 	MAS_CUDA(c, cudaMemcpyAsync(in.p, xyz, sizeof(float) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
 	morton_points_kernel<<<cdiv(count, 256), 256, 0, c->stream>>>(in.p, count, codes.p);
 	MAS_CUDA(c, cudaMemcpyAsync(out, codes.p, sizeof(unsigned long long) * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
 	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
-	release(in);
-	release(codes);
 	return MAS_OK;
 }
 
