@@ -95,7 +95,11 @@ enum
 	 * buffers still take the copy engine.  Measured on a virtualised B200 host whose copy engine reads host memory at
 	 * 15-20 GB/s while SM loads reach 33 GB/s and D2H runs at 56 GB/s either way (tools/pcie_bound.py); z always returns
 	 * through the copy engine.  Results are bit-identical. */
-	MAS_OPT_HOST_PULL = 7
+	MAS_OPT_HOST_PULL = 7,
+	/* EXPERIMENTAL, default 0.  1: the batched inversion factorises each 16x16 diagonal tile in registers, redundantly on
+	 * every warp of the CTA, instead of one warp walking it through shared memory.  Same
+	 * operations in the same order: the packed inverses are bit-identical.  Takes effect at the next mas_prepare. */
+	MAS_OPT_INVERT_VARIANT = 8
 };
 
 /* mas_get_int keys */

@@ -97,6 +97,7 @@ struct Context
 	int optAlignCuts = 1;
 	int optStencilFix = 0;       // read eeSets / vfSets from their own index 0 and form the third VF weight from b0 + b1 (Q2/Q3 fixed)
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
+	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
 	int optHostPull = 0;         // host-pointer apply: pull a page-locked residual with a kernel instead of the copy engine
 	int allocateCalls = 0;
 	int rank = 0, world = 1;
