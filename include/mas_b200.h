@@ -96,9 +96,11 @@ enum
 	 * 15-20 GB/s while SM loads reach 33 GB/s and D2H runs at 56 GB/s either way (tools/pcie_bound.py); z always returns
 	 * through the copy engine.  Results are bit-identical. */
 	MAS_OPT_HOST_PULL = 7,
-	/* EXPERIMENTAL, default 0.  1: the batched inversion factorises each 16x16 diagonal tile in registers, redundantly on
-	 * every warp of the CTA, instead of one warp walking it through shared memory.  Same
-	 * operations in the same order: the packed inverses are bit-identical.  Takes effect at the next mas_prepare. */
+	/* EXPERIMENTAL, default 0; a bit mask.  Bit 0: the batched inversion factorises each 16x16 diagonal tile in registers,
+	 * redundantly on every warp of the CTA, instead of one warp walking it through shared memory (same operations in the
+	 * same order: bit-identical inverses).  Bit 1: the final product E^T D^-1 E runs on the tensor cores as 3xTF32
+	 * (hi/lo split, three m16n8k8 MMAs per product, FP32 accumulation), which holds the parity tolerance where plain TF32
+	 * does not.  Takes effect at the next mas_prepare. */
 	MAS_OPT_INVERT_VARIANT = 8
 };
 

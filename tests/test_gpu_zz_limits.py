@@ -97,7 +97,7 @@ import os  # noqa: E402
 @pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="experimental kernels: set MAS_EXPERIMENTAL=1")
 @pytest.mark.parametrize("name", ["cloth64", "cloth96_stiff", "tet16x16x8", "cloth96_collisions"])
 def test_experimental_invert_variant_is_bit_identical(name, gpu_cls, synth):
-    """MAS_OPT_INVERT_VARIANT 1 (register-resident diagonal-tile factorisation on every warp) performs the reference's
+    """MAS_OPT_INVERT_VARIANT bit 0 (register-resident diagonal-tile factorisation on every warp) performs the reference's
     operations in the reference's order, like the shipped variant: every packed inverse must match bit for bit."""
     def coll():
         m = synth.cloth(96, with_topology=True)
@@ -117,3 +117,16 @@ def test_experimental_invert_variant_is_bit_identical(name, gpu_cls, synth):
             assert np.array_equal(ia, ib), blk
         else:
             assert np.abs(ia - ib).max() <= 1e-5 * np.abs(ia).max(), blk
+
+
+@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="experimental kernels: set MAS_EXPERIMENTAL=1")
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("name", ["cloth64", "cloth96_collisions", "tet16x16x8", "cloth200_stiff", "chain100_fragmented_banks"])
+def test_experimental_tensor_core_product_holds_the_parity_bar(name, variant, gpu_cls, synth, oracle_lib):
+    """MAS_OPT_INVERT_VARIANT bit 1: E^T D^-1 E as 3xTF32 MMAs.  Not bit-identical to the FP32 kernel, but it has to pass
+    the very same parity test (structure bit-exact, inverses and z within the FP64-arbitrated bars)."""
+    def with_variant(device):
+        g = gpu_cls(device)
+        g.set_option(8, variant)
+        return g
+    _structure_and_apply(name, with_variant, synth, oracle_lib)
