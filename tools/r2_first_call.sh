@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of a new round: everything that was written without a GPU gets measured in one go.
+#   gpurun --timeout 900 -- 'bash tools/r2_first_call.sh'
+# Results land in gpurun_out/r2_*.  Order: cheap and decisive first.
+mkdir -p gpurun_out
+# 1. the experimental inversion variants: parity (gated tests) and setup time against the shipped kernel
+MAS_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_limits.py -m gpu -q -x > gpurun_out/r2_experimental_tests.log 2>&1
+echo "experimental tests rc=$?" | tee -a gpurun_out/r2_summary.txt
+timeout 120 python tools/invert_variant_bench.py > gpurun_out/r2_invert_variants.json 2> gpurun_out/r2_invert_variants.err
+tail -1 gpurun_out/r2_invert_variants.json | tee -a gpurun_out/r2_summary.txt
+# 2. the bench line (now with both host stagings in e2e) and the reference arm
+timeout 400 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
+tail -c 600 gpurun_out/r2_bench_1gpu.json | tee -a gpurun_out/r2_summary.txt
+timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2_bench_reference.json 2>/dev/null
+# 3. PCIe staging on this box
+timeout 60 python tools/pcie_bound.py > gpurun_out/r2_pcie_bound.json 2>/dev/null
+# 4. the whole GPU suite
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2_gpu_tests.log 2>&1
+echo "gpu suite rc=$?" | tee -a gpurun_out/r2_summary.txt
+tail -3 gpurun_out/r2_gpu_tests.log | tee -a gpurun_out/r2_summary.txt
