@@ -388,6 +388,23 @@ def cloth_with_duplicate_edges(n: int = 24, every: int = 5) -> Mesh:
                       name=f"cloth{n}+dup")
 
 
+def random_cloud(n: int = 1500, k_nearest: int = 5, seed: int = 3, box=(1.0, 0.7, 0.4)) -> Mesh:
+    """An irregular 3-D mesh: n points uniform in a box, every point connected to its `k_nearest` nearest neighbours
+    (symmetrised, each undirected edge once, ascending (a, b)).  Unlike the lattices, degrees vary from vertex to vertex,
+    Morton banks cut through the connectivity anywhere and several components per bank are the rule — the shape of a
+    mesher's tetrahedral output.  scipy is test-side tooling only."""
+    from scipy.spatial import cKDTree
+    rng = np.random.RandomState(seed)
+    pos = (rng.uniform(0.0, 1.0, size=(n, 3)) * np.asarray(box)).astype(np.float32)
+    _, nbr = cKDTree(pos.astype(np.float64)).query(pos.astype(np.float64), k=k_nearest + 1)
+    a = np.repeat(np.arange(n), k_nearest)
+    b = nbr[:, 1:].reshape(-1)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    pairs = np.unique(np.stack([lo, hi], 1), axis=0)
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    return from_edges(pos, pairs[:, 0], pairs[:, 1], name=f"cloud{n}k{k_nearest}s{seed}")
+
+
 def residual(nv: int, seed: int = 1) -> np.ndarray:
     """r ~ U(-1,1) per component, MT19937(seed), xyz per vertex in order; w = 0."""
     rng = np.random.RandomState(seed)

@@ -21,6 +21,17 @@ def test_ties_and_duplicate_neighbours_vs_oracle(name, gpu_cls, synth, oracle_li
     _structure_and_apply(name, gpu_cls, synth, oracle_lib)
 
 
+@pytest.mark.parametrize("args", [(1500, 5, 3), (4000, 7, 4), (900, 3, 5), (2500, 10, 6)])
+def test_irregular_point_clouds_vs_oracle(args, gpu_cls, synth, oracle_lib, monkeypatch):
+    """Random 3-D points joined to their k nearest neighbours: degrees from 3 to 19, Morton banks that cut through the
+    connectivity anywhere.  tests/test_oracle_vs_reference.py pins the oracle to the compiled reference on the same four
+    meshes; here the CUDA path has to match the oracle (integers bit for bit, inverses and z within the parity bars)."""
+    import test_gpu_parity as tp
+    name = "cloud%d_k%d" % args[:2]
+    monkeypatch.setattr(tp, "_cases", lambda s: {name: lambda: synth.random_cloud(*args)})
+    _structure_and_apply(name, gpu_cls, synth, oracle_lib)
+
+
 def test_one_vertex_over_the_five_level_limit_is_refused(gpu_cls, pkg):
     """32^5 + 1 vertices need a sixth level, which the Int4 ancestor table (SeSchwarzPreconditioner.h:96) cannot hold: the
     reference would overrun it; the C ABI returns MAS_ERR_UNSUPPORTED before touching any input."""

@@ -52,6 +52,11 @@ CASES = {
     "chain1_single_vertex": lambda s: s.chain(1),               # no edges at all
     "chain32_exactly_one_bank": lambda s: s.chain(32),
     "cloth24_duplicate_edges": lambda s: s.cloth_with_duplicate_edges(24),   # repeated neighbour indices: blocks add up
+    # irregular 3-D meshes (random points, k nearest neighbours): varying degrees, banks cut through the connectivity
+    "cloud1500_k5": lambda s: s.random_cloud(1500, 5, 3),
+    "cloud4000_k7": lambda s: s.random_cloud(4000, 7, 4),
+    "cloud900_k3_two_levels": lambda s: s.random_cloud(900, 3, 5),            # 149 level-1 nodes under a 2-level hierarchy
+    "cloud2500_k10": lambda s: s.random_cloud(2500, 10, 6),
     # chain(33) / chain(100) (fragmented banks on a tiny mesh) are NOT run through the compiled reference: its fixed-size
     # allocation (pad32(nv)/32 * 1.5 nodes per level, cpp:112-135, Q6) is overrun by their level-1 counts and it corrupts the
     # heap (observed: intermittent segfault).  tests/test_gpu_parity.py runs them against the oracle, whose buffers follow
