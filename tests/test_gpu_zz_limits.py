@@ -32,6 +32,17 @@ def test_irregular_point_clouds_vs_oracle(args, gpu_cls, synth, oracle_lib, monk
     _structure_and_apply(name, gpu_cls, synth, oracle_lib)
 
 
+@pytest.mark.parametrize("n", [64, 96])
+def test_rippled_cloth_with_fragmented_banks_vs_oracle(n, gpu_cls, synth, oracle_lib, monkeypatch):
+    """A 1e-4 out-of-plane ripple gets the full weight of the z bits of the Morton code (per-axis normalisation, cpp:225):
+    banks hold several components each, level 1 is 4-5 times larger than on the flat sheet and the top level keeps several
+    nodes.  The reference overruns its fixed allocation on such input from 512^2 on (Q6); buffers here follow the counts."""
+    import test_gpu_parity as tp
+    name = f"rippled{n}"
+    monkeypatch.setattr(tp, "_cases", lambda s: {name: lambda: synth.rippled_cloth(n)})
+    _structure_and_apply(name, gpu_cls, synth, oracle_lib)
+
+
 def test_one_vertex_over_the_five_level_limit_is_refused(gpu_cls, pkg):
     """32^5 + 1 vertices need a sixth level, which the Int4 ancestor table (SeSchwarzPreconditioner.h:96) cannot hold: the
     reference would overrun it; the C ABI returns MAS_ERR_UNSUPPORTED before touching any input."""

@@ -52,6 +52,9 @@ CASES = {
     "chain1_single_vertex": lambda s: s.chain(1),               # no edges at all
     "chain32_exactly_one_bank": lambda s: s.chain(32),
     "cloth24_duplicate_edges": lambda s: s.cloth_with_duplicate_edges(24),   # repeated neighbour indices: blocks add up
+    # faint out-of-plane ripple: per-axis Morton normalisation fragments the banks (554 level-1 nodes instead of 128, a top
+    # level of 6 nodes); still inside the reference's fixed 1.5x allocation at this size (Q6 bites from 512^2)
+    "rippled64_fragmented_banks": lambda s: s.rippled_cloth(64),
     # irregular 3-D meshes (random points, k nearest neighbours): varying degrees, banks cut through the connectivity
     "cloud1500_k5": lambda s: s.random_cloud(1500, 5, 3),
     "cloud4000_k7": lambda s: s.random_cloud(4000, 7, 4),
