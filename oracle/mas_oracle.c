@@ -403,8 +403,9 @@ static void build_hierarchy(Oracle* o)
 	o->levelSize[1][0] = n1;
 	o->levelSize[1][1] = nVC;
 
-	uint32_t* nextMask = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(nv > 32 ? nv : 32));
-	int* nextId = (int*)malloc(sizeof(int) * (size_t)(nv > 32 ? nv : 32));
+	/* a level never has more nodes than the one below; masks are cleared in whole banks (pad32(cnt) <= nVC) */
+	uint32_t* nextMask = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)nVC + 32));
+	int* nextId = (int*)malloc(sizeof(int) * ((size_t)nVC + 32));
 	for (int level = 1; level < L; ++level)
 	{
 		const int cnt = o->levelSize[level][0], begin = o->levelSize[level][1];

@@ -418,6 +418,15 @@ def rippled_cloth(n: int = 64, amplitude: float = 1e-4, k: float = 1000.0) -> Me
     return from_edges(pos, a, b, k=k, name=f"rippled{n}")
 
 
+def dust(n: int = 6000, seed: int = 2, m: float = 1.0) -> Mesh:
+    """n free particles, no edges at all: nothing ever aggregates, so EVERY level keeps n one-vertex clusters (three
+    times the reference's whole fixed allocation at n = 6000, Q6) and every domain matrix is m I.  Known answer without
+    any reference: z = min(numLevel, 4) r / m."""
+    rng = np.random.RandomState(seed)
+    pos = rng.uniform(0.0, 1.0, size=(n, 3)).astype(np.float32)
+    return from_edges(pos, np.zeros(0, np.int64), np.zeros(0, np.int64), m=m, name=f"dust{n}")
+
+
 def residual(nv: int, seed: int = 1) -> np.ndarray:
     """r ~ U(-1,1) per component, MT19937(seed), xyz per vertex in order; w = 0."""
     rng = np.random.RandomState(seed)

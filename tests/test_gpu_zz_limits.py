@@ -4,6 +4,7 @@ here does not mask the parity, PCG and sharded suites under `pytest -x`."""
 import numpy as np
 import pytest
 
+from helpers import assert_structure_equal, make_oracle
 from test_gpu_parity import gpu_cls, test_structure_and_apply_vs_oracle as _structure_and_apply  # noqa: F401
 
 pytestmark = pytest.mark.gpu
@@ -41,6 +42,22 @@ def test_rippled_cloth_with_fragmented_banks_vs_oracle(n, gpu_cls, synth, oracle
     name = f"rippled{n}"
     monkeypatch.setattr(tp, "_cases", lambda s: {name: lambda: synth.rippled_cloth(n)})
     _structure_and_apply(name, gpu_cls, synth, oracle_lib)
+
+
+def test_edge_free_particles_grow_every_level(gpu_cls, synth, oracle_lib):
+    """6000 free particles: every level keeps 6000 one-vertex clusters (the node arrays have to grow past their first
+    guess of nv + nv/8 + 4096) and every domain matrix is the identity: structure equals the oracle's, z = 3 r exactly."""
+    mesh = synth.dust(6000)
+    g = gpu_cls(0).setup_from_mesh(mesh)
+    o = make_oracle(oracle_lib, mesh)
+    assert_structure_equal(g, o, mesh.nv)
+    assert g.level_size().tolist() == [[0, 0], [6000, 6016], [6000, 12032], [6000, 18048]]
+    r = synth.residual(mesh.nv)
+    z = np.full_like(r, 5.0)
+    g.Preconditioning(z, r)
+    assert np.array_equal(z[:, :3], np.float32(3) * r[:, :3]) and np.all(z[:, 3] == 0)
+    for b in (0, 187, 188, 400, g.num_blocks - 1):
+        assert np.array_equal(g.dense_inverse(b), np.eye(96, dtype=np.float32))
 
 
 def test_one_vertex_over_the_five_level_limit_is_refused(gpu_cls, pkg):

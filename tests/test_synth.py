@@ -31,3 +31,16 @@ def test_device_cloth_generator_on_gpu_matches_numpy(synth):
     for x, y in ((a.positions, b.positions), (a.nbr_starts, b.nbr_starts), (a.nbr_idx, b.nbr_idx), (a.offdiag, b.offdiag),
                  (a.diag, b.diag)):
         assert np.array_equal(x, y.cpu().numpy())
+
+
+def test_oracle_known_answer_on_edge_free_particles(oracle_lib, synth):
+    """No edges: nothing aggregates, every level keeps nv one-vertex clusters (far beyond the reference's fixed 1.5x
+    allocation, so the compiled reference cannot run this) and every domain matrix is the mass block: z = numLevel * r."""
+    from helpers import make_oracle
+    mesh = synth.dust(6000)
+    o = make_oracle(oracle_lib, mesh)
+    assert o.num_level == 3
+    assert o.level_size().tolist() == [[0, 0], [6000, 6016], [6000, 12032], [6000, 18048]]
+    r = synth.residual(mesh.nv)
+    z = o.apply(r)
+    assert np.array_equal(z[:, :3], np.float32(3) * r[:, :3]) and np.all(z[:, 3] == 0)
