@@ -55,6 +55,10 @@ CASES = {
     # faint out-of-plane ripple: per-axis Morton normalisation fragments the banks (554 level-1 nodes instead of 128, a top
     # level of 6 nodes); still inside the reference's fixed 1.5x allocation at this size (Q6 bites from 512^2)
     "rippled64_fragmented_banks": lambda s: s.rippled_cloth(64),
+    "tet13x9x7_odd_dimensions": lambda s: s.tet_cube(13, 9, 7),
+    "cloth_strip3x200": lambda s: s.cloth_rect(3, 200),
+    "cloth33_saturated_with_collisions": lambda s: s.add_collisions(s.cloth(33, with_topology=True), 2000, 2000, 2000, seed=22),
+    "cloth33_many_isolated_vertices": lambda s: s.cloth_with_isolated_vertices(33, 40),   # top level keeps 42 nodes
     # irregular 3-D meshes (random points, k nearest neighbours): varying degrees, banks cut through the connectivity
     "cloud1500_k5": lambda s: s.random_cloud(1500, 5, 3),
     "cloud4000_k7": lambda s: s.random_cloud(4000, 7, 4),
