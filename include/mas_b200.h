@@ -100,7 +100,8 @@ enum
 	 * redundantly on every warp of the CTA, instead of one warp walking it through shared memory (same operations in the
 	 * same order: bit-identical inverses).  Bit 1: the final product E^T D^-1 E runs on the tensor cores as 3xTF32
 	 * (hi/lo split, three m16n8k8 MMAs per product, FP32 accumulation), which holds the parity tolerance where plain TF32
-	 * does not.  Takes effect at the next mas_prepare. */
+	 * does not.  Value 4: the whole blocked inversion on the tensor cores (panel products and trailing
+	 * updates as 3xTF32 MMAs too, the matrix held in accumulator fragments).  Takes effect at the next mas_prepare. */
 	MAS_OPT_INVERT_VARIANT = 8
 };
 

@@ -208,7 +208,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:
-		if (value < 0 || value > 3) return fail(h, MAS_ERR_INVALID, "unknown inversion variant");
+		if (value < 0 || value > 4) return fail(h, MAS_ERR_INVALID, "unknown inversion variant");
 		h->optInvertVariant = value;
 		return MAS_OK;   // takes effect at the next mas_prepare
 	case MAS_OPT_HOST_PULL: h->optHostPull = value ? 1 : 0; return MAS_OK;   // staging only: the apply graph stays valid

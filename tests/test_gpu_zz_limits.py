@@ -159,11 +159,12 @@ def test_experimental_invert_variant_is_bit_identical(name, gpu_cls, synth):
 
 
 @pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="experimental kernels: set MAS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("name", ["cloth64", "cloth96_collisions", "tet16x16x8", "cloth200_stiff", "chain100_fragmented_banks"])
 def test_experimental_tensor_core_product_holds_the_parity_bar(name, variant, gpu_cls, synth, oracle_lib):
-    """MAS_OPT_INVERT_VARIANT bit 1: E^T D^-1 E as 3xTF32 MMAs.  Not bit-identical to the FP32 kernel, but it has to pass
-    the very same parity test (structure bit-exact, inverses and z within the FP64-arbitrated bars)."""
+    """MAS_OPT_INVERT_VARIANT bit 1: E^T D^-1 E as 3xTF32 MMAs; value 4: the whole blocked inversion on the tensor cores.
+    Not bit-identical to the FP32 kernel, but they have to pass the very same parity test (structure bit-exact, inverses
+    and z within the FP64-arbitrated bars)."""
     def with_variant(device):
         g = gpu_cls(device)
         g.set_option(8, variant)
