@@ -94,7 +94,9 @@ enum
 	 * cudaPointerGetAttributes) a kernel PULLS it through its device mapping with coalesced 16-byte loads instead; pageable
 	 * buffers still take the copy engine.  Measured on a virtualised B200 host whose copy engine reads host memory at
 	 * 15-20 GB/s while SM loads reach 33 GB/s and D2H runs at 56 GB/s either way (tools/pcie_bound.py); z always returns
-	 * through the copy engine.  Results are bit-identical. */
+	 * through the copy engine.  Results are bit-identical.  2: decide by measurement — the first six host-pointer applies
+	 * with a page-locked residual time both stagings on the device (three each), the faster one is kept
+	 * (mas_get_int(MAS_INT_HOST_PULL_CHOICE): -1 undecided, 0 copy engine, 1 kernel pull). */
 	MAS_OPT_HOST_PULL = 7,
 	/* EXPERIMENTAL, default 0; a bit mask.  Bit 0: the batched inversion factorises each 16x16 diagonal tile in registers,
 	 * redundantly on every warp of the CTA, instead of one warp walking it through shared memory (same operations in the
@@ -122,7 +124,8 @@ enum
 	MAS_INT_PCG_LAUNCHES_PER_ITER = 11, /* kernels per iteration of the last mas_pcg_solve (its own 4 + the apply's) */
 	MAS_INT_PCG_CONVERGED = 12,    /* 1 if the last mas_pcg_solve met its tolerance */
 	MAS_INT_PEER_ERROR = 13,       /* 1 if a peer-memory wait ever timed out (a rank stopped publishing) */
-	MAS_INT_ALIGNED_CUTS = 14      /* sharded contexts: 1 if no level-1 bank straddles a shard cut (the apply exchanges level-2 residuals) */
+	MAS_INT_ALIGNED_CUTS = 14,     /* sharded contexts: 1 if no level-1 bank straddles a shard cut (the apply exchanges level-2 residuals) */
+	MAS_INT_HOST_PULL_CHOICE = 15  /* MAS_OPT_HOST_PULL = 2: -1 still sampling, 0 copy engine kept, 1 kernel pull kept */
 };
 
 /* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */

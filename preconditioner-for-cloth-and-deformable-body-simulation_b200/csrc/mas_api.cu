@@ -149,6 +149,8 @@ int mas_create(mas_handle_t* out, int device)
 	cudaEventCreate(&c->evAp1);
 	cudaEventCreate(&c->evF0);
 	cudaEventCreate(&c->evF1);
+	cudaEventCreate(&c->evS0);
+	cudaEventCreate(&c->evS1);
 	cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evHead, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evCoarse, cudaEventDisableTiming);
@@ -175,6 +177,8 @@ int mas_destroy(mas_handle_t h)
 	if (h->evAp1) cudaEventDestroy(h->evAp1);
 	if (h->evF0) cudaEventDestroy(h->evF0);
 	if (h->evF1) cudaEventDestroy(h->evF1);
+	if (h->evS0) cudaEventDestroy(h->evS0);
+	if (h->evS1) cudaEventDestroy(h->evS1);
 	if (h->evFork) cudaEventDestroy(h->evFork);
 	if (h->evHead) cudaEventDestroy(h->evHead);
 	if (h->evCoarse) cudaEventDestroy(h->evCoarse);
@@ -211,7 +215,11 @@ int mas_set_option(mas_handle_t h, int key, int value)
 		if (value < 0 || value > 4) return fail(h, MAS_ERR_INVALID, "unknown inversion variant");
 		h->optInvertVariant = value;
 		return MAS_OK;   // takes effect at the next mas_prepare
-	case MAS_OPT_HOST_PULL: h->optHostPull = value ? 1 : 0; return MAS_OK;   // staging only: the apply graph stays valid
+	case MAS_OPT_HOST_PULL:   // staging only: the apply graph stays valid
+		if (value < 0 || value > 2) return fail(h, MAS_ERR_INVALID, "MAS_OPT_HOST_PULL takes 0, 1 or 2");
+		h->optHostPull = value;
+		h->pullCalls = 0; h->pullChoice = -1; h->pullBestMs[0] = h->pullBestMs[1] = 1e30f;
+		return MAS_OK;
 	default: return fail(h, MAS_ERR_INVALID, "unknown option");
 	}
 	drop_graph(h);
@@ -411,7 +419,13 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
 	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
 	const float4* mapped = c->optHostPull ? mapped_host_pointer(residual) : nullptr;
-	if (mapped)
+	// auto mode (2): the first six applies with a page-locked residual time the two stagings (three each, the first of each
+	// is warm-up) with CUDA events on the stream; the faster one is kept for the rest of the context's life
+	const bool sampling = mapped && c->optHostPull == 2 && c->pullChoice < 0;
+	const int samplePull = sampling ? (c->pullCalls >= 3 ? 1 : 0) : 0;
+	const bool pull = mapped && (c->optHostPull == 1 || (sampling ? samplePull == 1 : c->pullChoice == 1));
+	if (sampling) MAS_CUDA(c, cudaEventRecord(c->evS0, c->stream));
+	if (pull)
 	{
 		int grid = cdiv(c->nv, 4 * 256);
 		if (grid > 32 * c->smCount) grid = 32 * c->smCount;
@@ -420,10 +434,18 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	}
 	else
 		MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, sizeof(float4) * (size_t)c->nv, cudaMemcpyHostToDevice, c->stream));
+	if (sampling) MAS_CUDA(c, cudaEventRecord(c->evS1, c->stream));
 	if (int rc = run_apply_device(c, c->rIn.p, c->zOut.p)) return rc;
 	// a shard only produces its own vertices' z; copy everything, the caller merges shards
 	MAS_CUDA(c, cudaMemcpyAsync(z, c->zOut.p, sizeof(float4) * (size_t)c->nv, cudaMemcpyDeviceToHost, c->stream));
 	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (sampling)
+	{
+		float ms = 0.f;
+		MAS_CUDA(c, cudaEventElapsedTime(&ms, c->evS0, c->evS1));
+		if (c->pullCalls % 3 != 0 && ms < c->pullBestMs[samplePull]) c->pullBestMs[samplePull] = ms;
+		if (++c->pullCalls >= 6) c->pullChoice = c->pullBestMs[1] < c->pullBestMs[0] ? 1 : 0;
+	}
 	return MAS_OK;
 }
 
@@ -573,6 +595,7 @@ int mas_get_int(mas_handle_t h, int key, long long* out)
 	case MAS_INT_PCG_LAUNCHES_PER_ITER: *out = c->pcgLaunchesPerIter; break;
 	case MAS_INT_PCG_CONVERGED: *out = c->pcgConverged; break;
 	case MAS_INT_ALIGNED_CUTS: *out = c->alignedCuts ? 1 : 0; break;
+	case MAS_INT_HOST_PULL_CHOICE: *out = c->pullChoice; break;
 	case MAS_INT_PEER_ERROR:
 	{
 		*out = 0;

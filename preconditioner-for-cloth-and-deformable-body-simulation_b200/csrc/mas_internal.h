@@ -98,7 +98,10 @@ struct Context
 	int optStencilFix = 0;       // read eeSets / vfSets from their own index 0 and form the third VF weight from b0 + b1 (Q2/Q3 fixed)
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
-	int optHostPull = 0;         // host-pointer apply: pull a page-locked residual with a kernel instead of the copy engine
+	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
+	int pullCalls = 0;           // auto mode: host-pointer applies sampled so far (3 per staging, the first of each is warm-up)
+	int pullChoice = -1;         // auto mode: -1 undecided, 0 copy engine, 1 kernel pull
+	float pullBestMs[2] = { 1e30f, 1e30f };
 	int allocateCalls = 0;
 	int rank = 0, world = 1;
 	int smCount = 148;
@@ -190,6 +193,7 @@ struct Context
 	cudaEvent_t evA = nullptr, evB = nullptr;      // prepare
 	cudaEvent_t evAp0 = nullptr, evAp1 = nullptr;  // whole apply (timed mode)
 	cudaEvent_t evF0 = nullptr, evF1 = nullptr;    // level-0 solve kernel (timed mode)
+	cudaEvent_t evS0 = nullptr, evS1 = nullptr;    // residual staging of the host-pointer apply (MAS_OPT_HOST_PULL = 2)
 	cudaStream_t sideA = nullptr, sideB = nullptr; // branches of the apply graph
 	cudaEvent_t evFork = nullptr, evHead = nullptr, evCoarse = nullptr, evTail = nullptr;
 	float lastApplyMs = 0.f, lastPrepareMs = 0.f;

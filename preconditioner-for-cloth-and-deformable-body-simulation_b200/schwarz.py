@@ -24,7 +24,7 @@ MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
  OPT_RESORT_PERIOD, OPT_HOST_PULL, OPT_INVERT_VARIANT) = range(9)
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
  INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
- INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS) = range(15)
+ INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS, INT_HOST_PULL_CHOICE) = range(16)
 (ARR_MORTON, ARR_SORTED_GET_ORIGINAL, ARR_ORIGINAL_GET_SORTED, ARR_GOING_NEXT, ARR_LEVEL_SIZE, ARR_FINE_CONNECT_MASK,
  ARR_COARSE_SPACE_TABLE, ARR_COARSE_TABLES, ARR_SORTED_ADJ_STARTS, ARR_SORTED_ADJ_IDX, ARR_STENCILS,
  ARR_STENCIL_INDEX_MAPPED, ARR_DENSE_INVERSE, ARR_MAPPED_R, ARR_MAPPED_Z, ARR_AABB) = range(16)

@@ -127,6 +127,13 @@ def test_host_pull_staging_is_bit_identical(gpu_cls, synth):
     z_pageable = np.full_like(r_np, 3.0)
     g.Preconditioning(z_pageable, r_np)                   # pageable r: copy engine even with the option on
     assert np.array_equal(z_pageable, z_ce.numpy())
+    g.set_option(7, 2)                                    # auto: six sampled applies, then one staging is kept
+    assert g.get_int(15) == -1
+    for _ in range(7):
+        z_auto = torch.full_like(r_pin, -1.0).pin_memory()
+        g.Preconditioning(z_auto, r_pin)
+        assert torch.equal(z_auto, z_ce)
+    assert g.get_int(15) in (0, 1)
     g.set_option(7, 0)
 
 
