@@ -104,7 +104,12 @@ enum
 	 * (hi/lo split, three m16n8k8 MMAs per product, FP32 accumulation), which holds the parity tolerance where plain TF32
 	 * does not.  Value 4: the whole blocked inversion on the tensor cores (panel products and trailing
 	 * updates as 3xTF32 MMAs too, the matrix held in accumulator fragments).  Takes effect at the next mas_prepare. */
-	MAS_OPT_INVERT_VARIANT = 8
+	MAS_OPT_INVERT_VARIANT = 8,
+	/* Host-pointer mas_apply only, default 0.  1: a PAGEABLE residual / z buffer (std::vector, malloc) is page-locked where it
+	 * lies with cudaHostRegister the first time it is seen, so that every later copy runs at pinned-memory speed; up to
+	 * four ranges per context, unlocked by mas_destroy or by setting the option back to 0.  The caller must keep such a
+	 * buffer allocated until then (the reference's callers reuse r and z for the whole solve). */
+	MAS_OPT_REGISTER_HOST = 9
 };
 
 /* mas_get_int keys */

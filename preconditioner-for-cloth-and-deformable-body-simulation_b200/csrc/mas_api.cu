@@ -80,6 +80,40 @@ static const float4* mapped_host_pointer(const void* host)
 	return reinterpret_cast<const float4*>(at.devicePointer);
 }
 
+// MAS_OPT_REGISTER_HOST: page-lock a pageable caller buffer where it lies, once, so that later copies run at pinned speed.
+// At most four ranges per context (r and z of a solver, twice); the oldest is unlocked when a fifth shows up.
+static void unregister_host_ranges(Context* c)
+{
+	for (auto& r : c->registered)
+	{
+		if (r.p) cudaHostUnregister(const_cast<void*>(r.p));
+		r.p = nullptr;
+		r.bytes = 0;
+	}
+	cudaGetLastError();
+}
+
+static void register_host_range(Context* c, const void* p, size_t bytes)
+{
+	for (const auto& r : c->registered)
+		if (r.p == p && r.bytes >= bytes) return;
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+	if (at.type != cudaMemoryTypeUnregistered) return;                 // already page-locked (or not host memory at all)
+	if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return; }
+	Context::HostRange* slot = nullptr;
+	for (auto& r : c->registered)
+		if (!r.p) { slot = &r; break; }
+	if (!slot)
+	{
+		cudaHostUnregister(const_cast<void*>(c->registered[0].p));
+		for (int k = 0; k + 1 < 4; ++k) c->registered[k] = c->registered[k + 1];
+		slot = &c->registered[3];
+	}
+	slot->p = p;
+	slot->bytes = bytes;
+}
+
 static void drop_graph(Context* c)
 {
 	if (c->applyGraph)
@@ -106,6 +140,7 @@ static void free_all(Context* c)
 {
 	drop_graph(c);
 	close_peers(c);
+	unregister_host_ranges(c);
 	release(c->arena); release(c->cutInfo);
 	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
 	release(c->aabb); release(c->code); release(c->codeSorted); release(c->s2o); release(c->o2s); release(c->iota);
@@ -215,6 +250,10 @@ int mas_set_option(mas_handle_t h, int key, int value)
 		if (value < 0 || value > 4) return fail(h, MAS_ERR_INVALID, "unknown inversion variant");
 		h->optInvertVariant = value;
 		return MAS_OK;   // takes effect at the next mas_prepare
+	case MAS_OPT_REGISTER_HOST:
+		h->optRegisterHost = value ? 1 : 0;
+		if (!value) unregister_host_ranges(h);
+		return MAS_OK;
 	case MAS_OPT_HOST_PULL:   // staging only: the apply graph stays valid
 		if (value < 0 || value > 2) return fail(h, MAS_ERR_INVALID, "MAS_OPT_HOST_PULL takes 0, 1 or 2");
 		h->optHostPull = value;
@@ -418,6 +457,11 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
 	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
+	if (c->optRegisterHost)
+	{
+		register_host_range(c, residual, sizeof(float4) * (size_t)c->nv);
+		register_host_range(c, z, sizeof(float4) * (size_t)c->nv);
+	}
 	const float4* mapped = c->optHostPull ? mapped_host_pointer(residual) : nullptr;
 	// auto mode (2): the first six applies with a page-locked residual time the two stagings (three each, the first of each
 	// is warm-up) with CUDA events on the stream; the faster one is kept for the rest of the context's life

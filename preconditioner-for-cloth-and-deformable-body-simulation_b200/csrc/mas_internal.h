@@ -99,6 +99,9 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
+	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
+	struct HostRange { const void* p = nullptr; size_t bytes = 0; };
+	HostRange registered[4];     // ranges this context page-locked (and must unlock)
 	int pullCalls = 0;           // auto mode: host-pointer applies sampled so far (3 per staging, the first of each is warm-up)
 	int pullChoice = -1;         // auto mode: -1 undecided, 0 copy engine, 1 kernel pull
 	float pullBestMs[2] = { 1e30f, 1e30f };

@@ -177,3 +177,25 @@ def test_experimental_tensor_core_product_holds_the_parity_bar(name, variant, gp
         g.set_option(8, variant)
         return g
     _structure_and_apply(name, with_variant, synth, oracle_lib)
+
+
+@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="unmeasured option: set MAS_EXPERIMENTAL=1")
+def test_register_host_option_keeps_results(gpu_cls, synth):
+    """MAS_OPT_REGISTER_HOST page-locks the caller's pageable r / z where they lie; results are unchanged, with and without
+    the kernel pull, and the ranges are released when the option is cleared."""
+    mesh = synth.cloth(96)
+    g = gpu_cls(0).setup_from_mesh(mesh)
+    r = synth.residual(mesh.nv)
+    z0 = np.zeros_like(r)
+    g.Preconditioning(z0, r)
+    g.set_option(9, 1)
+    for pull in (0, 1):
+        g.set_option(7, pull)
+        for _ in range(3):
+            z = np.full_like(r, 9.0)
+            g.Preconditioning(z, r)
+            assert np.array_equal(z, z0)
+    g.set_option(9, 0)
+    z = np.zeros_like(r)
+    g.Preconditioning(z, r)
+    assert np.array_equal(z, z0)
