@@ -188,14 +188,16 @@ def test_register_host_option_keeps_results(gpu_cls, synth):
     r = synth.residual(mesh.nv)
     z0 = np.zeros_like(r)
     g.Preconditioning(z0, r)
+    z = np.zeros_like(r)                  # the contract: registered buffers stay allocated until the option is cleared
     g.set_option(9, 1)
     for pull in (0, 1):
         g.set_option(7, pull)
         for _ in range(3):
-            z = np.full_like(r, 9.0)
+            z[:] = 9.0
             g.Preconditioning(z, r)
             assert np.array_equal(z, z0)
     g.set_option(9, 0)
-    z = np.zeros_like(r)
+    g.set_option(7, 0)
+    z[:] = 9.0
     g.Preconditioning(z, r)
     assert np.array_equal(z, z0)
