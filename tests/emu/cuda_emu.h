@@ -1,0 +1,112 @@
+// TEST INFRASTRUCTURE ONLY.  One CUDA thread block played by OS threads, for running device code of csrc/*.cuh on the CPU:
+// every CUDA thread is a std::thread, __syncthreads / __syncwarp / named warp barriers are std::barrier objects, warp shuffles
+// and the m16n8k8 TF32 MMA exchange their operands through per-warp scratch (fragment layouts of the PTX ISA), TF32
+// conversion rounds to 10 mantissa bits (ties away from zero, like cvt.rna).  Arithmetic intrinsics map to fmaf & co., so
+// FP32 results equal the GPU's wherever the GPU code uses the IEEE intrinsics.  Data races are NOT detected; this checks
+// logic and indexing, not synchronisation.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>   // float4, make_float4, the __device__ / __forceinline__ decorations as no-ops for g++
+
+namespace emu {
+
+struct Dim { unsigned x = 0, y = 0, z = 0; };
+inline thread_local Dim tid;
+inline Dim bdim;
+
+struct Block
+{
+	int nThreads;
+	std::barrier<> all;
+	std::vector<std::unique_ptr<std::barrier<>>> warp;
+	std::vector<float> shfl;            // [warp][lane]
+	std::vector<unsigned> fragA, fragB; // [warp][lane][4], [warp][lane][2]
+	explicit Block(int n) : nThreads(n), all(n), shfl((size_t)n), fragA((size_t)n * 4), fragB((size_t)n * 2)
+	{
+		for (int w = 0; w < n / 32; ++w) warp.emplace_back(new std::barrier<>(32));
+	}
+};
+inline Block* block = nullptr;
+
+inline void run(int nThreads, const std::function<void()>& kernel)
+{
+	Block b(nThreads);
+	block = &b;
+	bdim.x = (unsigned)nThreads; bdim.y = bdim.z = 1;
+	std::vector<std::thread> th;
+	for (int t = 0; t < nThreads; ++t)
+		th.emplace_back([t, &kernel] { tid.x = (unsigned)t; kernel(); });
+	for (auto& x : th) x.join();
+	block = nullptr;
+}
+
+}  // namespace emu
+
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+#define threadIdx (::emu::tid)
+#define blockDim (::emu::bdim)
+
+inline void __syncthreads() { emu::block->all.arrive_and_wait(); }
+inline void emu_warp_barrier() { emu::block->warp[emu::tid.x >> 5]->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier(); }
+
+inline float __shfl_sync(unsigned, float v, int src)
+{
+	const unsigned w = emu::tid.x >> 5;
+	emu::block->shfl[emu::tid.x] = v;
+	emu_warp_barrier();
+	const float r = emu::block->shfl[32 * w + (src & 31)];
+	emu_warp_barrier();
+	return r;
+}
+
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+
+// cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 explicit mantissa bits; low 13 bits cleared
+inline unsigned emu_cvt_rna_tf32(float x)
+{
+	unsigned u = __float_as_uint(x);
+	if ((u & 0x7f800000u) == 0x7f800000u) return u;
+	u += 0x1000u;
+	return u & ~0x1fffu;
+}
+
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32: D = A B + D over one warp.
+//   A (16x8, row): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)          g = lane / 4, t = lane % 4
+//   B (8x8, col) : b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   C/D (16x8)   : c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)
+inline void emu_mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+	const unsigned w = emu::tid.x >> 5, lane = emu::tid.x & 31, g = lane >> 2, t = lane & 3;
+	unsigned* A = emu::block->fragA.data() + (size_t)w * 32 * 4;
+	unsigned* B = emu::block->fragB.data() + (size_t)w * 32 * 2;
+	for (int u = 0; u < 4; ++u) A[4 * lane + u] = a[u];
+	for (int u = 0; u < 2; ++u) B[2 * lane + u] = b[u];
+	emu_warp_barrier();
+	auto Ael = [&](unsigned row, unsigned k) { return __uint_as_float(A[4 * ((row & 7) * 4 + (k & 3)) + (row >> 3) + 2 * (k >> 2)]); };
+	auto Bel = [&](unsigned k, unsigned n) { return __uint_as_float(B[2 * (n * 4 + (k & 3)) + (k >> 2)]); };
+	for (int u = 0; u < 4; ++u)
+	{
+		const unsigned row = g + 8 * (u >> 1), col = 2 * t + (u & 1);
+		float acc = d[u];
+		for (unsigned k = 0; k < 8; ++k) acc = std::fmaf(Ael(row, k), Bel(k, col), acc);
+		d[u] = acc;
+	}
+	emu_warp_barrier();
+}
