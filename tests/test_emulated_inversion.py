@@ -61,3 +61,28 @@ def test_register_factorisation_is_bit_identical_to_the_shipped_kernel(emulator,
     H = blocks[0]
     assert np.array_equal(emulator(0, H), emulator(1, H))             # bit 0 changes where the arithmetic happens, not what
     assert np.array_equal(emulator(2, H), emulator(3, H))
+
+
+def test_no_shared_memory_race_under_thread_sanitizer(tmp_path):
+    """The same emulation built with -fsanitize=thread: CUDA threads are OS threads and __syncthreads / __syncwarp / named
+    barriers are the only ordering between them, exactly the CUDA memory model for shared memory, so a missing barrier in the
+    device code shows up as a ThreadSanitizer data race (checked by deleting one: 110 reports).  All variants must be clean."""
+    if not shutil.which("g++") or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "invert_emu_tsan")
+    build = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-I", CUDA_INC, "-I",
+                            os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tests", "emu", "invert_emu.cpp"), "-o", exe],
+                           capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + build.stderr[-200:])
+    rng = np.random.RandomState(0)
+    b = rng.randn(96, 96)
+    a = (b @ b.T + 96 * np.eye(96)).astype(np.float32)
+    a[93:, :] = 0
+    a[:, 93:] = 0                                                       # one padding node (identity path)
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
+    for variant in range(5):
+        p = subprocess.run([exe, str(variant)], input=np.int32(1).tobytes() + a.tobytes(), capture_output=True, timeout=900, env=env)
+        assert p.returncode == 0, p.stderr[-500:]
+        races = p.stderr.decode(errors="replace").count("WARNING: ThreadSanitizer: data race")
+        assert races == 0, (variant, races, p.stderr.decode(errors="replace")[:1500])
