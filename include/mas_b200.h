@@ -109,7 +109,12 @@ enum
 	 * lies with cudaHostRegister the first time it is seen, so that every later copy runs at pinned-memory speed; up to
 	 * four ranges per context, unlocked by mas_destroy or by setting the option back to 0.  The caller must keep such a
 	 * buffer allocated until then (the reference's callers reuse r and z for the whole solve). */
-	MAS_OPT_REGISTER_HOST = 9
+	MAS_OPT_REGISTER_HOST = 9,
+	/* Incremental setup, default 0.  1: a PreparePreconditioner without collision stencils that follows
+	 * another one without stencils keeps the clustering (levels, goingNext, coarse tables, shard cuts): it depends on the
+	 * sorted adjacency and the stencils only, so the rebuilt one would be identical bit for bit.  Assembly and inversion
+	 * always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds. */
+	MAS_OPT_CACHE_HIERARCHY = 10
 };
 
 /* mas_get_int keys */

@@ -243,7 +243,8 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_APPLY_VARIANT: h->optApplyVariant = value; break;
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
-	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; break;
+	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
+	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:
@@ -333,6 +334,7 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 		MAS_CUDA(c, cudaMemsetAsync(c->arena.p, 0, bytes, c->stream));
 		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
+	c->hierarchyCached = false;
 	if (int rc = order_vertices(c, dPos, dStarts, dIdx)) return rc;
 	c->allocated = true;
 	c->prepared = false;
@@ -368,7 +370,14 @@ int mas_prepare_begin(mas_handle_t h, const float* diagonal, const float* csrOff
 		if (int rc = stage_in(c, c->vfIn, vfSets, vfBytes, mem, &dVf)) return rc;
 	}
 	if (int rc = build_stencils(c, dEf, dEe, dVf, efTotal, eeTotal, vfTotal)) return rc;
-	if (int rc = build_hierarchy(c)) return rc;
+	// The clustering depends on the sorted adjacency (fixed since mas_allocate) and on the stencils only: without stencils
+	// two consecutive prepares build the same hierarchy, bit for bit (MAS_OPT_CACHE_HIERARCHY skips the second build).
+	if (!(c->optCacheHierarchy && c->hierarchyCached && c->nStencil == 0))
+	{
+		c->hierarchyCached = false;
+		if (int rc = build_hierarchy(c)) return rc;
+		c->hierarchyCached = c->nStencil == 0;
+	}
 
 	if (c->p2p && (size_t)c->nCoarseNodes > c->arenaCap)
 		return fail(c, MAS_ERR_UNSUPPORTED, "coarse hierarchy larger than the peer arena: use the begin/exchange/end protocol");

@@ -99,6 +99,8 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
+	int optCacheHierarchy = 0;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
+	bool hierarchyCached = false;   // the hierarchy in this context was built without stencils for the current ordering / options
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
 	struct HostRange { const void* p = nullptr; size_t bytes = 0; };
 	HostRange registered[4];     // ranges this context page-locked (and must unlock)
