@@ -4,7 +4,7 @@
 # Results land in gpurun_out/r2_*.  Order: cheap and decisive first.
 mkdir -p gpurun_out
 # 1. the experimental inversion variants: parity (gated tests) and setup time against the shipped kernel
-MAS_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_zz_limits.py -m gpu -q -x > gpurun_out/r2_experimental_tests.log 2>&1
+MAS_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_zz_limits.py -m gpu -q -rA > gpurun_out/r2_experimental_tests.log 2>&1
 echo "experimental tests rc=$?" | tee -a gpurun_out/r2_summary.txt
 timeout 120 python tools/invert_variant_bench.py > gpurun_out/r2_invert_variants.json 2> gpurun_out/r2_invert_variants.err
 tail -1 gpurun_out/r2_invert_variants.json | tee -a gpurun_out/r2_summary.txt
