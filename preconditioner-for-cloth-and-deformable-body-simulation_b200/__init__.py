@@ -1,7 +1,8 @@
 """B200-native multilevel additive Schwarz (MAS) preconditioner: drop-in for the one hot path of
 V-Sekai/preconditioner-for-cloth-and-deformable-body-simulation (class SE::SeSchwarzPreconditioner).
 
-  csrc/           hand-written sm_100a CUDA kernels + the extern "C" boundary (include/mas_b200.h)
+  csrc/           hand-written sm_100a CUDA kernels + the extern "C" boundary (include/mas_b200.h); the batched inversion's
+                  device code (mas_invert.cuh) is also compiled for the host by tests/emu (thread-block emulation)
   schwarz.py      host-side mirror of the reference class over that C ABI (ctypes)
   synth.py        deterministic synthetic inputs for the BASELINE.json configs
   pcg.py          caller-side PCG loop (the reference ships none) over mas_pcg_solve, used for iteration-count parity
