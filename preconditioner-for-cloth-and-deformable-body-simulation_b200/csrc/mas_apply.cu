@@ -32,6 +32,10 @@ constexpr int kApplyThreads = 256;
 constexpr int kWarpsPerCta = kApplyThreads / 32;
 
 // streaming 128-bit load: read-only path, no L1 allocation (each byte is used once)
+#ifdef MAS_CPU_EMULATION   // tests/emu/apply_emu.cpp compiles the kernels of this file for the host (test infrastructure)
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) { return *p; }
+__device__ __forceinline__ float ldg_stream1(const float* p) { return *p; }
+#else
 __device__ __forceinline__ float4 ldg_stream4(const float4* p)
 {
 	float4 v;
@@ -44,6 +48,7 @@ __device__ __forceinline__ float ldg_stream1(const float* p)
 	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
 	return v;
 }
+#endif
 
 struct Vec3
 {
@@ -228,6 +233,7 @@ struct PeerArgs
 	int world, rank;
 };
 
+#ifndef MAS_CPU_EMULATION   // the peer exchange needs several GPUs: not part of the host emulation
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
 {
 	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -306,6 +312,8 @@ __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int firs
 		}
 	}
 }
+
+#endif  // MAS_CPU_EMULATION
 
 // One 32-node group of coarse nodes [begin + 32*bank, ...): sum R over the nodes that share a parent and store it
 // (BuildResidualHierarchy level l -> l+1, cpp:1577-1591)
@@ -514,6 +522,7 @@ __global__ void add_coarse_kernel(const int* __restrict__ s2o, const int* __rest
 
 }  // namespace
 
+#ifndef MAS_CPU_EMULATION   // host side: launches (the emulation has its own launcher)
 // number of levels CollectFinalZ prolongs: l = 1 .. min(numLevel,4)-1 (cpp:1710, Q4) unless the fix is requested
 static int prolonged_top(const Context* c)
 {
@@ -762,5 +771,7 @@ int prioritize_apply_graph(Context* c, cudaGraph_t graph)
 	}
 	return MAS_OK;
 }
+
+#endif  // MAS_CPU_EMULATION
 
 }  // namespace mas

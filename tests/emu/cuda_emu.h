@@ -20,7 +20,7 @@ namespace emu {
 
 struct Dim { unsigned x = 0, y = 0, z = 0; };
 inline thread_local Dim tid;
-inline Dim bdim;
+inline Dim bdim, bid, gdim;
 
 struct Block
 {
@@ -28,8 +28,9 @@ struct Block
 	std::barrier<> all;
 	std::vector<std::unique_ptr<std::barrier<>>> warp;
 	std::vector<float> shfl;            // [warp][lane]
+	std::vector<unsigned> shflu;        // [warp][lane]
 	std::vector<unsigned> fragA, fragB; // [warp][lane][4], [warp][lane][2]
-	explicit Block(int n) : nThreads(n), all(n), shfl((size_t)n), fragA((size_t)n * 4), fragB((size_t)n * 2)
+	explicit Block(int n) : nThreads(n), all(n), shfl((size_t)n), shflu((size_t)n), fragA((size_t)n * 4), fragB((size_t)n * 2)
 	{
 		for (int w = 0; w < n / 32; ++w) warp.emplace_back(new std::barrier<>(32));
 	}
@@ -48,8 +49,27 @@ inline void run(int nThreads, const std::function<void()>& kernel)
 	block = nullptr;
 }
 
+// a whole grid, one block after the other (kernels without inter-block synchronisation)
+inline void launch(int grid, int nThreads, const std::function<void()>& kernel)
+{
+	gdim.x = (unsigned)grid; gdim.y = gdim.z = 1;
+	for (int b = 0; b < grid; ++b)
+	{
+		bid.x = (unsigned)b;
+		run(nThreads, kernel);
+	}
+}
+
 }  // namespace emu
 
+#define blockIdx (::emu::bid)
+#define gridDim (::emu::gdim)
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __global__
+#define __global__
+#undef __shared__
+#define __shared__ static      // one copy for all threads of the (single, sequentially emulated) block
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
@@ -69,6 +89,41 @@ inline float __shfl_sync(unsigned, float v, int src)
 	emu_warp_barrier();
 	return r;
 }
+
+inline unsigned emu_exchange(unsigned v, int src)
+{
+	const unsigned w = emu::tid.x >> 5;
+	emu::block->shflu[emu::tid.x] = v;
+	emu_warp_barrier();
+	const unsigned r = emu::block->shflu[32 * w + (src & 31)];
+	emu_warp_barrier();
+	return r;
+}
+inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_exchange(v, src); }
+inline int __shfl_sync(unsigned, int v, int src) { return (int)emu_exchange((unsigned)v, src); }
+inline float __shfl_xor_sync(unsigned m, float v, int mask) { return __shfl_sync(m, v, (int)((emu::tid.x & 31) ^ (unsigned)mask)); }
+inline unsigned __ballot_sync(unsigned, int pred)
+{
+	const unsigned w = emu::tid.x >> 5;
+	emu::block->shflu[emu::tid.x] = pred ? 1u : 0u;
+	emu_warp_barrier();
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) r |= emu::block->shflu[32 * w + l] << l;
+	emu_warp_barrier();
+	return r;
+}
+inline unsigned __match_any_sync(unsigned, int key)
+{
+	const unsigned w = emu::tid.x >> 5;
+	emu::block->shflu[emu::tid.x] = (unsigned)key;
+	emu_warp_barrier();
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) r |= (emu::block->shflu[32 * w + l] == (unsigned)key ? 1u : 0u) << l;
+	emu_warp_barrier();
+	return r;
+}
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline void __threadfence_block() {}
 
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
