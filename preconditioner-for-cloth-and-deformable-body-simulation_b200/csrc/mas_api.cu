@@ -190,11 +190,14 @@ int mas_create(mas_handle_t* out, int device)
 	cudaEventCreateWithFlags(&c->evHead, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evCoarse, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evTail, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->evChainFork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&c->evChainL1, cudaEventDisableTiming);
 	{
 		int prLow = 0, prHigh = 0;
 		cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
 		cudaStreamCreateWithPriority(&c->sideA, cudaStreamNonBlocking, prLow);
 		cudaStreamCreateWithPriority(&c->sideB, cudaStreamNonBlocking, prLow);
+		cudaStreamCreateWithPriority(&c->sideC, cudaStreamNonBlocking, prHigh);
 	}
 	*out = c;
 	return MAS_OK;
@@ -218,6 +221,9 @@ int mas_destroy(mas_handle_t h)
 	if (h->evHead) cudaEventDestroy(h->evHead);
 	if (h->evCoarse) cudaEventDestroy(h->evCoarse);
 	if (h->evTail) cudaEventDestroy(h->evTail);
+	if (h->evChainFork) cudaEventDestroy(h->evChainFork);
+	if (h->evChainL1) cudaEventDestroy(h->evChainL1);
+	if (h->sideC) cudaStreamDestroy(h->sideC);
 	if (h->sideA) cudaStreamDestroy(h->sideA);
 	if (h->sideB) cudaStreamDestroy(h->sideB);
 	delete h;
@@ -244,6 +250,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
+	case MAS_OPT_APPLY_CHAIN: h->optApplyChain = value ? 1 : 0; break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;

@@ -591,12 +591,28 @@ int apply_begin(Context* c, const float4* r)
 }
 
 // coarse levels: needs the complete level-1 residuals in coarseR (after the exchange when world > 1)
-static int launch_coarse(Context* c, cudaStream_t st)
+// `capturing`: called from apply_forked (stream capture), where MAS_OPT_APPLY_CHAIN may fork the level-1 solves off the chain.
+static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false)
 {
 	if (c->numLevel < 2) return MAS_OK;
 	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
 	const int nCoarseBlocks = c->nCoarseNodes / 32;
 	const bool l2x = exchange_level2(c);
+	// MAS_OPT_APPLY_CHAIN (experimental): the level-1 blocks (97 % of the coarse blocks) need nothing but the level-1
+	// residuals, which are complete once restrict_fine has run — on a sharded context with aligned cuts as well, because no
+	// level-1 bank straddles a cut.  Their solve is forked off here and runs BESIDE restrict_l1 -> [peer exchange] ->
+	// restrict_top -> solve of the levels >= 2, instead of after them; the chain rejoins before prolong_sum.
+	const int ownL1Blocks = c->l1BlockEnd - c->l1BlockBegin;
+	const bool forkL1 = capturing && c->optApplyChain && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (c->p2p && l2x));
+	if (forkL1)
+	{
+		MAS_CUDA(c, cudaEventRecord(c->evChainFork, st));
+		MAS_CUDA(c, cudaStreamWaitEvent(c->sideC, c->evChainFork, 0));
+		solve_coarse_kernel<<<ownL1Blocks, 128, 0, c->sideC>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri,
+			c->coarseR.p, c->coarseZ.p, c->l1BlockBegin, ownL1Blocks, c->nL1Blocks);
+		c->applyLaunches += 1;
+		MAS_CUDA(c, cudaEventRecord(c->evChainL1, c->sideC));
+	}
 	if (c->p2p && !(l2x && c->numLevel < 3))
 	{
 		const int first = l2x ? c->levelSize[2][1] - c->nVC : begin1 - c->nVC;
@@ -638,7 +654,19 @@ static int launch_coarse(Context* c, cudaStream_t st)
 	// redundantly on every rank, which removes any exchange of z
 	const int ownL1 = c->l1BlockEnd - c->l1BlockBegin;
 	const int solved = ownL1 + (nCoarseBlocks - c->nL1Blocks);
-	if (solved > 0)
+	if (forkL1)
+	{
+		const int tops = nCoarseBlocks - c->nL1Blocks;
+		if (tops > 0)
+		{
+			// ownL1 = 0: block index = topBegin + blockIdx.x, the blocks of levels >= 2 only
+			solve_coarse_kernel<<<tops, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
+				c->coarseZ.p, c->l1BlockBegin, 0, c->nL1Blocks);
+			c->applyLaunches += 1;
+		}
+		MAS_CUDA(c, cudaStreamWaitEvent(st, c->evChainL1, 0));
+	}
+	else if (solved > 0)
 	{
 		solve_coarse_kernel<<<solved, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
 			c->coarseZ.p, c->l1BlockBegin, ownL1, c->nL1Blocks);
@@ -724,7 +752,7 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		cudaStream_t saved = c->stream;
 		c->stream = st;
 		int rc = apply_begin(c, r);
-		if (rc == MAS_OK) rc = launch_coarse(c, st);
+		if (rc == MAS_OK) rc = launch_coarse(c, st, true);
 		c->stream = saved;
 		if (rc != MAS_OK) return rc;
 	}

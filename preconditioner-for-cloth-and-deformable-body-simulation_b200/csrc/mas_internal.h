@@ -99,6 +99,7 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
+	int optApplyChain = 0;       // 1: apply graph solves the level-1 blocks beside the rest of the coarse chain (experimental)
 	int optCacheHierarchy = 0;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
 	bool hierarchyCached = false;   // the hierarchy in this context was built without stencils for the current ordering / options
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
@@ -200,6 +201,8 @@ struct Context
 	cudaEvent_t evF0 = nullptr, evF1 = nullptr;    // level-0 solve kernel (timed mode)
 	cudaEvent_t evS0 = nullptr, evS1 = nullptr;    // residual staging of the host-pointer apply (MAS_OPT_HOST_PULL = 2)
 	cudaStream_t sideA = nullptr, sideB = nullptr; // branches of the apply graph
+	cudaStream_t sideC = nullptr;                  // MAS_OPT_APPLY_CHAIN: level-1 solves beside the chain
+	cudaEvent_t evChainFork = nullptr, evChainL1 = nullptr;
 	cudaEvent_t evFork = nullptr, evHead = nullptr, evCoarse = nullptr, evTail = nullptr;
 	float lastApplyMs = 0.f, lastPrepareMs = 0.f;
 };

@@ -12,6 +12,15 @@ tail -1 gpurun_out/r2_invert_variants.json | tee -a gpurun_out/r2_summary.txt
 timeout 400 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
 tail -c 600 gpurun_out/r2_bench_1gpu.json | tee -a gpurun_out/r2_summary.txt
 timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2_bench_reference.json 2>/dev/null
+for cfg in 0 1 2; do
+  timeout 200 python bench.py --config $cfg --lean --steps 200 --warmup 10 > gpurun_out/r2_chain0_cfg$cfg.json 2>/dev/null
+  timeout 200 python bench.py --config $cfg --lean --steps 200 --warmup 10 --apply-chain > gpurun_out/r2_chain1_cfg$cfg.json 2>/dev/null
+  python - <<PY | tee -a gpurun_out/r2_summary.txt
+import json
+a = json.loads(open("gpurun_out/r2_chain0_cfg$cfg.json").read().strip().splitlines()[-1]); b = json.loads(open("gpurun_out/r2_chain1_cfg$cfg.json").read().strip().splitlines()[-1])
+print("config $cfg: apply us shipped", round(a["ms_per_step"] * 1e3, 2), " MAS_OPT_APPLY_CHAIN", round(b["ms_per_step"] * 1e3, 2))
+PY
+done
 # 3. PCIe staging on this box
 timeout 60 python tools/pcie_bound.py > gpurun_out/r2_pcie_bound.json 2>/dev/null
 # 4. the whole GPU suite
