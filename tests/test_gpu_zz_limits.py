@@ -248,4 +248,3 @@ def test_apply_chain_fork_is_bit_identical(n, gpu_cls, synth):
         g.Preconditioning(z1, r)
     torch.cuda.synchronize()
     assert torch.equal(z0, z1)
-    assert g.apply_launches == (8 if g.num_level > 3 else 7) or g.apply_launches > 0
