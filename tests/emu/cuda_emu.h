@@ -123,6 +123,42 @@ inline unsigned __match_any_sync(unsigned, int key)
 	return r;
 }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __shfl_sync(unsigned m, unsigned long long, int) = delete;
+inline double __shfl_xor_sync(unsigned m, double v, int mask)
+{
+	unsigned long long u;
+	std::memcpy(&u, &v, 8);
+	const int src = (int)((emu::tid.x & 31) ^ (unsigned)mask);
+	const unsigned lo = emu_exchange((unsigned)u, src), hi = emu_exchange((unsigned)(u >> 32), src);
+	u = ((unsigned long long)hi << 32) | lo;
+	std::memcpy(&v, &u, 8);
+	return v;
+}
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+
+// atomics: CUDA threads of one block run concurrently here, so these are real atomics (compare-exchange loops)
+template <typename T>
+inline T emu_atomic_add(T* p, T v)
+{
+	T old;
+	__atomic_load(p, &old, __ATOMIC_RELAXED);
+	for (;;)
+	{
+		T want = old + v;
+		if (__atomic_compare_exchange(p, &old, &want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return old;
+	}
+}
+inline double atomicAdd(double* p, double v) { return emu_atomic_add(p, v); }
+inline float atomicAdd(float* p, float v) { return emu_atomic_add(p, v); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
+// dynamic shared memory of the block being emulated (blocks run one after the other)
+inline unsigned char* emu_dynamic_smem()
+{
+	alignas(128) static unsigned char buf[128 * 1024];
+	return buf;
+}
 inline void __threadfence_block() {}
 
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
