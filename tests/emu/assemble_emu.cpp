@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE ONLY.  The setup kernels of csrc/mas_assemble.cu — cross_bank, fine_assemble_invert, carry_up,
 // coarse_invert (and through them csrc/mas_invert.cuh) — run on the CPU through tests/emu/cuda_emu.h, launched in the order of
-// assemble_and_invert_begin + _end for a single-GPU context without collision stencils.
+// assemble_and_invert_begin + _end for a single-GPU context (collision_hessian included when stencils are given).
 //   assemble_emu < in.bin > out.bin
 //   in : int32 nv, numLevel, totalClusters, nnz, levelSize[(numLevel + 1) * 2]; int32 s2o[nv], adjStart[nv + 1], adjIdx[nnz],
-//        goingNext[totalClusters], ranges[nv + 1]; float32 diag[nv][9], offdiag[nnz][9]  (caller's arrays, original order)
+//        goingNext[totalClusters], ranges[nv + 1]; float32 diag[nv][9], offdiag[nnz][9]  (caller's arrays, original order);
+//        int32 nStencil; then nStencil 80-byte Stencil records and int32 stencilIndexMapped[nStencil][5]  (may be 0)
 //   out: float32 dense inverses [totalClusters / 32][96][96]
 #include "cuda_emu.h"
 
@@ -51,10 +52,36 @@ int main()
 			posTab[(size_t)(15 + i) * kInvThreads + t] = (unsigned short)(tr >= tc ? packed_pos(tr + 16 * i, tc + 16 * i) : 0);
 	}
 
+	const int nStencil = rd<int>(1)[0];
+	const auto stencils = rd<Stencil>((size_t)nStencil);
+	const auto stIdx = rd<int>((size_t)nStencil * 5);
+	std::vector<float> extraFine, cooVal;
+	std::vector<int> cooCount, cooStart, cooFill;
+	if (nStencil > 0)
+	{
+		extraFine.assign((size_t)nv * 9, 0.f);
+		cooCount.assign((size_t)nFine, 0); cooStart.assign((size_t)nFine, 0); cooFill.assign((size_t)nFine, 0);
+		CollisionArgs ca;
+		ca.st = stencils.data(); ca.stIdx = stIdx.data(); ca.nStencil = nStencil;
+		ca.goingNext = goingNext.data(); ca.numLevel = L; ca.nVC = nVC;
+		ca.ownBegin = 0; ca.ownEnd = nVC;
+		ca.extraFine = extraFine.data(); ca.dense = dense; ca.carry = carry;
+		ca.cooCount = cooCount.data(); ca.cooStart = nullptr; ca.cooFill = cooFill.data(); ca.cooVal = nullptr;
+		emu::launch(cdiv(nStencil, 256), 256, [&] { collision_hessian_kernel(ca, 0); });
+		int entries = 0;                                 // launch_exclusive_scan
+		for (int b = 0; b < nFine; ++b) { cooStart[b] = entries; entries += cooCount[b]; }
+		cooVal.assign((size_t)(entries > 0 ? entries : 1) * 10, 0.f);
+		ca.cooStart = cooStart.data(); ca.cooVal = cooVal.data();
+		emu::launch(cdiv(nStencil, 256), 256, [&] { collision_hessian_kernel(ca, 1); });
+	}
+
 	FineArgs fa;
 	fa.diag = diag.data(); fa.offdiag = offdiag.data(); fa.ranges = ranges.data();
 	fa.s2o = s2o.data(); fa.adjStart = adjStart.data(); fa.adjIdx = adjIdx.data(); fa.goingNext = goingNext.data();
-	fa.extraFine = nullptr; fa.cooStart = nullptr; fa.cooCount = nullptr; fa.cooVal = nullptr;
+	fa.extraFine = nStencil > 0 ? extraFine.data() : nullptr;
+	fa.cooStart = nStencil > 0 ? cooStart.data() : nullptr;
+	fa.cooCount = nStencil > 0 ? cooCount.data() : nullptr;
+	fa.cooVal = nStencil > 0 ? cooVal.data() : nullptr;
 	fa.dense = dense; fa.carry = carry;
 	fa.packedOut = packed.data();
 	fa.posTab = posTab.data();

@@ -32,7 +32,11 @@ def _run(exe, o, mesh, env=None):
     starts, idx = o.sorted_adjacency()
     parts = [np.array([mesh.nv, o.num_level, tc, mesh.nnz], np.int32), np.ascontiguousarray(o.level_size(), np.int32),
              o.sorted_get_original().astype(np.int32), starts.astype(np.int32), idx.astype(np.int32), o.going_next()[:tc].astype(np.int32),
-             np.asarray(mesh.nbr_starts, np.int32), np.ascontiguousarray(mesh.diag, np.float32), np.ascontiguousarray(mesh.offdiag, np.float32)]
+             np.asarray(mesh.nbr_starts, np.int32), np.ascontiguousarray(mesh.diag, np.float32), np.ascontiguousarray(mesh.offdiag, np.float32),
+             np.array([o.stencil_num], np.int32)]
+    if o.stencil_num:
+        st, mapped = o.stencils()
+        parts += [np.frombuffer(st.tobytes(), np.uint8), np.ascontiguousarray(mapped, np.int32)]
     p = subprocess.run([exe], input=b"".join(x.tobytes() for x in parts), capture_output=True, timeout=1800, env=env)
     assert p.returncode == 0, p.stderr[-800:]
     return np.frombuffer(p.stdout, np.float32).reshape(tc // 32, 96, 96), p.stderr.decode(errors="replace")
@@ -51,6 +55,7 @@ CASES = {
     "cloud900_irregular": lambda s: s.random_cloud(900, 3, 5),
     "cloth40_skewed_blocks": lambda s: s.cloth(40, skew=0.05),
     "chain100_fragmented": lambda s: s.chain(100),
+    "cloth40_collisions": lambda s: s.add_collisions(s.cloth(40, with_topology=True), 100, 100, 200, seed=7),
 }
 
 
@@ -74,6 +79,7 @@ def test_emulated_setup_has_no_race_under_thread_sanitizer(tmp_path, synth, orac
     if p.returncode != 0:
         pytest.skip("ThreadSanitizer runtime not available: " + p.stderr[-200:])
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
-    for mesh in (synth.tet_cube(8, 8, 4), synth.cloth_with_duplicate_edges(24)):
+    for mesh in (synth.tet_cube(8, 8, 4), synth.cloth_with_duplicate_edges(24),
+                 synth.add_collisions(synth.cloth(24, with_topology=True), 60, 60, 120, seed=3)):
         _, err = _run(exe, make_oracle(oracle_lib, mesh, "f"), mesh, env)
         assert err.count("WARNING: ThreadSanitizer: data race") == 0, err[:2000]
