@@ -331,6 +331,7 @@ __global__ void find_cuts_kernel(const int* __restrict__ bankPrefix, int nBanks,
 
 }  // namespace
 
+#ifndef MAS_CPU_EMULATION   // host side: launches (tests/emu/cluster_emu.cpp, test infrastructure, has its own launcher)
 int launch_exclusive_scan(Context* c, const int* in, int count, int* out, int* totalOut)
 {
 	exclusive_scan_kernel<<<1, kScanThreads, 0, c->stream>>>(in, count, out, totalOut);
@@ -523,5 +524,7 @@ int build_hierarchy(Context* c)
 	MAS_CUDA(c, cudaGetLastError());
 	return MAS_OK;
 }
+
+#endif  // MAS_CPU_EMULATION
 
 }  // namespace mas

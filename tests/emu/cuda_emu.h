@@ -37,28 +37,33 @@ struct Block
 };
 inline Block* block = nullptr;
 
-inline void run(int nThreads, const std::function<void()>& kernel)
+// A whole grid, one block after the other (kernels without inter-block synchronisation).  The OS threads are created once
+// per launch and walk through the blocks together: `edge` separates consecutive blocks (a thread that returns early from the
+// kernel waits there), `all` is the kernel's own __syncthreads.
+inline void launch(int grid, int nThreads, const std::function<void()>& kernel)
 {
 	Block b(nThreads);
+	std::barrier<> edge(nThreads);
 	block = &b;
 	bdim.x = (unsigned)nThreads; bdim.y = bdim.z = 1;
+	gdim.x = (unsigned)grid; gdim.y = gdim.z = 1;
 	std::vector<std::thread> th;
 	for (int t = 0; t < nThreads; ++t)
-		th.emplace_back([t, &kernel] { tid.x = (unsigned)t; kernel(); });
+		th.emplace_back([t, grid, &kernel, &edge] {
+			tid.x = (unsigned)t;
+			for (int blk = 0; blk < grid; ++blk)
+			{
+				if (t == 0) bid.x = (unsigned)blk;
+				edge.arrive_and_wait();
+				kernel();
+				edge.arrive_and_wait();
+			}
+		});
 	for (auto& x : th) x.join();
 	block = nullptr;
 }
 
-// a whole grid, one block after the other (kernels without inter-block synchronisation)
-inline void launch(int grid, int nThreads, const std::function<void()>& kernel)
-{
-	gdim.x = (unsigned)grid; gdim.y = gdim.z = 1;
-	for (int b = 0; b < grid; ++b)
-	{
-		bid.x = (unsigned)b;
-		run(nThreads, kernel);
-	}
-}
+inline void run(int nThreads, const std::function<void()>& kernel) { launch(1, nThreads, kernel); }
 
 }  // namespace emu
 
@@ -123,6 +128,34 @@ inline unsigned __match_any_sync(unsigned, int key)
 	return r;
 }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __shfl_up_sync(unsigned, int v, int delta)
+{
+	const int lane = (int)(emu::tid.x & 31);
+	const int r = (int)emu_exchange((unsigned)v, lane >= delta ? lane - delta : lane);
+	return r;
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v)      // every lane passes the mask of its own group
+{
+	const unsigned w = emu::tid.x >> 5;
+	emu::block->shflu[emu::tid.x] = v;
+	emu_warp_barrier();
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l)
+		if ((mask >> l) & 1u) r |= emu::block->shflu[32 * w + l];
+	emu_warp_barrier();
+	return r;
+}
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v)
+{
+	unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+	while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+	return old;
+}
 inline int __shfl_sync(unsigned m, unsigned long long, int) = delete;
 inline double __shfl_xor_sync(unsigned m, double v, int mask)
 {
