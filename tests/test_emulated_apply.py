@@ -51,7 +51,7 @@ CASES = {
     "rippled64_fragmented": lambda s: s.rippled_cloth(64),
     "stacked2x24_ties": lambda s: s.stacked_cloth(24, 2),
     "dust1025_no_edges": lambda s: s.dust(1025),
-    "cloth160_four_levels": lambda s: s.cloth(160),
+    "cloth182_four_levels": lambda s: s.cloth(182),                      # 33,124 vertices: restrict_top runs
 }
 
 
@@ -73,7 +73,7 @@ def test_emulated_apply_has_no_race_under_thread_sanitizer(tmp_path, synth, orac
     exe, p = _build(tmp_path, extra=("-fsanitize=thread",))
     if p.returncode != 0:
         pytest.skip("ThreadSanitizer runtime not available: " + p.stderr[-200:])
-    mesh = synth.cloth(160)                                    # four levels: every kernel of the chain runs
+    mesh = synth.cloth(64)                                     # three levels: restrict_fine / _l1, solve_coarse, prolong_sum, solve_fine
     o = make_oracle(oracle_lib, mesh, "f")
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=0")
     run = subprocess.run([exe], input=_input(o, mesh, synth.residual(mesh.nv)), capture_output=True, timeout=1800, env=env)
