@@ -12,8 +12,10 @@
 #include "mas_internal.h"
 
 #include <cfloat>
+#ifndef MAS_CPU_EMULATION   // tests/emu/order_emu.cpp compiles the kernels of this file for the host (test infrastructure)
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#endif
 
 namespace mas {
 
@@ -149,6 +151,7 @@ __global__ void remap_adjacency_kernel(const int* __restrict__ s2o, const int* _
 
 }  // namespace
 
+#ifndef MAS_CPU_EMULATION   // host side: launches and the CUB sort / scan
 int order_vertices(Context* c, const float4* positions, const int* inStarts, const int* inIdx)
 {
 	const int nv = c->nv;
@@ -207,5 +210,7 @@ int morton_encode_points(Context* c, const float* xyz, int count, unsigned long 
 	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
 	return MAS_OK;
 }
+
+#endif  // MAS_CPU_EMULATION
 
 }  // namespace mas

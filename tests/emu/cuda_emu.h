@@ -106,6 +106,11 @@ inline unsigned emu_exchange(unsigned v, int src)
 }
 inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu_exchange(v, src); }
 inline int __shfl_sync(unsigned, int v, int src) { return (int)emu_exchange((unsigned)v, src); }
+inline float __shfl_down_sync(unsigned m, float v, int delta)
+{
+	const int lane = (int)(emu::tid.x & 31);
+	return __shfl_sync(m, v, lane + delta < 32 ? lane + delta : lane);
+}
 inline float __shfl_xor_sync(unsigned m, float v, int mask) { return __shfl_sync(m, v, (int)((emu::tid.x & 31) ^ (unsigned)mask)); }
 inline unsigned __ballot_sync(unsigned, int pred)
 {
