@@ -265,7 +265,7 @@ def run_ours(args):
     if args.variant is not None:
         g.set_option(1, args.variant)
     if args.apply_chain:
-        g.set_option(11, 1)                         # experimental: level-1 solves forked off the coarse chain (MAS_OPT_APPLY_CHAIN)
+        g.set_option(11, args.apply_chain)                         # experimental: level-1 solves forked off the coarse chain (MAS_OPT_APPLY_CHAIN)
     if args.invert_variant:
         g.set_option(8, args.invert_variant)       # experimental inversion kernels (MAS_OPT_INVERT_VARIANT); default 0
     p2p = False
@@ -527,7 +527,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
     ap.add_argument("--variant", type=int, default=None, help="MAS_OPT_APPLY_VARIANT override (development sweeps)")
-    ap.add_argument("--apply-chain", action="store_true", help="MAS_OPT_APPLY_CHAIN=1 (experimental apply graph shape)")
+    ap.add_argument("--apply-chain", type=int, default=0, help="MAS_OPT_APPLY_CHAIN bit mask (experimental apply graph shapes; 0 = shipped)")
     ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT (experimental setup kernels; 0 = shipped)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")

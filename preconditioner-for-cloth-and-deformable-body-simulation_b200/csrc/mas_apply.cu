@@ -603,7 +603,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false)
 	// level-1 bank straddles a cut.  Their solve is forked off here and runs BESIDE restrict_l1 -> [peer exchange] ->
 	// restrict_top -> solve of the levels >= 2, instead of after them; the chain rejoins before prolong_sum.
 	const int ownL1Blocks = c->l1BlockEnd - c->l1BlockBegin;
-	const bool forkL1 = capturing && c->optApplyChain && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (c->p2p && l2x));
+	const bool forkL1 = capturing && (c->optApplyChain & 1) && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (c->p2p && l2x));
 	if (forkL1)
 	{
 		MAS_CUDA(c, cudaEventRecord(c->evChainFork, st));
@@ -623,20 +623,23 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false)
 		gather_peers_kernel<<<grid, 256, 0, st>>>(peer_args(c), first, count, c->coarseR.p);
 		c->applyLaunches += 1;
 	}
-	if (c->numLevel > 2 && !l2x)
+	// MAS_OPT_APPLY_CHAIN bit 1 (experimental): on small single-GPU meshes (at most 16 level-1 banks) the one-CTA kernel that
+	// walks the top levels starts at level 1 already, which takes restrict_l1 — one launch — off the latency-bound chain
+	const bool topFromL1 = (c->optApplyChain & 2) && c->world == 1 && c->numLevel > 2 && cnt1 <= 512;
+	if (c->numLevel > 2 && !l2x && !topFromL1)
 	{
 		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, 0,
 			cdiv(cnt1, 32), c->coarseR.p, nullptr, 0ull, nullptr);
 		c->applyLaunches += 1;
 	}
-	if (c->numLevel > 3)
+	if (c->numLevel > 3 || topFromL1)
 	{
 		TopArgs a;
-		a.numLevel = c->numLevel; a.nVC = c->nVC; a.firstLevel = 2;
+		a.numLevel = c->numLevel; a.nVC = c->nVC; a.firstLevel = topFromL1 ? 1 : 2;
 		for (int l = 0; l <= kMaxLevel; ++l) { a.count[l] = 0; a.begin[l] = 0; }
 		for (int l = 1; l <= c->numLevel; ++l) { a.count[l] = c->levelSize[l][0]; a.begin[l] = c->levelSize[l][1]; }
 		const int cnt2 = c->levelSize[2][0];
-		if (cnt2 > 2048)
+		if (cnt2 > 2048 && !topFromL1)
 		{
 			// a large level 2 (meshes beyond ~2M vertices): level 2 -> 3 on many CTAs, the single CTA takes over from level 3
 			restrict_l1_kernel<<<cdiv(cdiv(cnt2, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, c->levelSize[2][1], cnt2, c->nVC, 0,

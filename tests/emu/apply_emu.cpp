@@ -55,18 +55,19 @@ int main()
 		// launch_coarse
 		const int cnt1 = ls[2], begin1 = ls[3];
 		const int nCoarseBlocks = nCoarse / 32, nL1Blocks = pad32(cnt1) / 32;
-		if (L > 2)
+		const bool topFromL1 = getenv("MAS_EMU_TOP_FROM_L1") && L > 2 && cnt1 <= 512;     // MAS_OPT_APPLY_CHAIN bit 1
+		if (L > 2 && !topFromL1)
 			emu::launch(cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, [&] {
 				restrict_l1_kernel(goingNext.data(), begin1, cnt1, nVC, 0, cdiv(cnt1, 32), coarseR.data(), nullptr, 0ull, nullptr);
 			});
-		if (L > 3)
+		if (L > 3 || topFromL1)
 		{
 			TopArgs a;
-			a.numLevel = L; a.nVC = nVC; a.firstLevel = 2;
+			a.numLevel = L; a.nVC = nVC; a.firstLevel = topFromL1 ? 1 : 2;
 			for (int l = 0; l <= kMaxLevel; ++l) { a.count[l] = 0; a.begin[l] = 0; }
 			for (int l = 1; l <= L; ++l) { a.count[l] = ls[2 * l]; a.begin[l] = ls[2 * l + 1]; }
 			const int cnt2 = ls[4];
-			if (cnt2 > 2048)
+			if (cnt2 > 2048 && !topFromL1)
 			{
 				emu::launch(cdiv(cdiv(cnt2, 32), kWarpsPerCta), kApplyThreads, [&] {
 					restrict_l1_kernel(goingNext.data(), ls[5], cnt2, nVC, 0, cdiv(cnt2, 32), coarseR.data(), nullptr, 0ull, nullptr);

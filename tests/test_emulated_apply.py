@@ -69,6 +69,19 @@ def test_emulated_apply_matches_the_oracle(name, emulator, synth, oracle_lib):
     assert rel_l2(z, z32) <= 3 * e_ref + 1e-5
 
 
+@pytest.mark.parametrize("name", ["cloth64_three_levels", "cloth50_ragged", "rippled64_fragmented"])
+def test_emulated_apply_with_the_top_walk_starting_at_level_1(name, emulator, synth, oracle_lib):
+    """MAS_OPT_APPLY_CHAIN bit 1 (experimental): restrict_top takes over from level 1 on small meshes instead of restrict_l1;
+    same sums over the same groups, so z is bit-identical to the shipped launch sequence (rippled64 has 554 level-1 nodes:
+    over the limit, the option must change nothing)."""
+    mesh = CASES[name](synth)
+    o32 = make_oracle(oracle_lib, mesh, "f")
+    data = _input(o32, mesh, synth.residual(mesh.nv, 2))
+    a = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True).stdout
+    b = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True, env=dict(os.environ, MAS_EMU_TOP_FROM_L1="1")).stdout
+    assert a == b and len(a) == 16 * mesh.nv
+
+
 def test_emulated_apply_has_no_race_under_thread_sanitizer(tmp_path, synth, oracle_lib):
     exe, p = _build(tmp_path, extra=("-fsanitize=thread",))
     if p.returncode != 0:

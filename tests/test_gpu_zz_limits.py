@@ -233,17 +233,19 @@ def test_cached_hierarchy_gives_identical_setup(gpu_cls, synth):
 
 
 @pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="unmeasured option: set MAS_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mask", [1, 2, 3])
 @pytest.mark.parametrize("n", [64, 192, 512])
-def test_apply_chain_fork_is_bit_identical(n, gpu_cls, synth):
-    """MAS_OPT_APPLY_CHAIN: the level-1 solves run beside the rest of the coarse chain in the apply graph; same kernels on
-    the same data, so z must not change by a bit (graph path = device pointers)."""
+def test_apply_chain_fork_is_bit_identical(n, mask, gpu_cls, synth):
+    """MAS_OPT_APPLY_CHAIN: bit 0 = the level-1 solves run beside the rest of the coarse chain in the apply graph, bit 1 = the
+    one-CTA top walk starts at level 1 on small meshes; same kernels on the same data, so z must not change by a bit (graph
+    path = device pointers)."""
     import torch
     mesh = synth.cloth(n)
     g = gpu_cls(0).setup_from_mesh(mesh, device_inputs=True)
     r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
     z0, z1 = torch.empty_like(r), torch.empty_like(r)
     g.Preconditioning(z0, r)
-    g.set_option(11, 1)
+    g.set_option(11, mask)
     for _ in range(3):
         g.Preconditioning(z1, r)
     torch.cuda.synchronize()
