@@ -115,7 +115,9 @@ enum
 	 * sorted adjacency and the stencils only, so the rebuilt one would be identical bit for bit.  Assembly and inversion
 	 * always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds. */
 	MAS_OPT_CACHE_HIERARCHY = 10,
-	/* EXPERIMENTAL, default 0; a bit mask.  Bit 1: on small single-GPU meshes (at most 512 level-1 nodes) the one-CTA kernel
+	/* EXPERIMENTAL, default 0; a bit mask.  Bit 2: when the whole level-0 solve runs beside the coarse chain (small meshes),
+	 * the kernel that adds the coarse part afterwards walks each vertex's ancestors itself, as CollectFinalZ does (cpp:1698-1719),
+	 * and prolong_sum leaves the chain.  Bit 1: on small single-GPU meshes (at most 512 level-1 nodes) the one-CTA kernel
 	 * that restricts the top levels starts at level 1, one launch less on the latency-bound chain.  Bit 0: in the apply graph
 	 * the level-1 blocks (97 % of the coarse blocks; they need only the
 	 * level-1 residuals) are solved BESIDE restrict_l1 -> [peer exchange] -> restrict_top -> solve of the levels >= 2 instead

@@ -251,7 +251,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
 	case MAS_OPT_APPLY_CHAIN:
-		if (value < 0 || value > 3) return fail(h, MAS_ERR_INVALID, "MAS_OPT_APPLY_CHAIN is a mask of bits 0 and 1");
+		if (value < 0 || value > 7) return fail(h, MAS_ERR_INVALID, "MAS_OPT_APPLY_CHAIN is a mask of bits 0, 1 and 2");
 		h->optApplyChain = value;
 		break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;

@@ -520,6 +520,26 @@ __global__ void add_coarse_kernel(const int* __restrict__ s2o, const int* __rest
 	z[ov] = make_float4(y.x, y.y, y.z, 0.f);
 }
 
+// MAS_OPT_APPLY_CHAIN bit 2 (experimental): the same addition without prolong_sum — every vertex walks its own ancestors
+// (CollectFinalZ as the reference writes it, cpp:1698-1719, through the Int4 ancestor table) and adds Z_1 + Z_2 + ... in
+// prolong_sum's order, so the result is bit-identical while one launch leaves the latency-bound chain.  Used when the whole
+// level-0 solve fits in the head of the apply graph (small meshes), where this kernel is all that follows the chain.
+__global__ void add_coarse_walk_kernel(const int* __restrict__ s2o, const int4* __restrict__ coarseTables, const float4* __restrict__ coarseZ,
+	int vBegin, int vEnd, int nVC, int levels, float4* __restrict__ z)
+{
+	const int v = vBegin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= vEnd) return;
+	const int ov = s2o[v];
+	const int4 a = coarseTables[v];
+	float4 c = coarseZ[a.x - nVC];
+	if (levels > 1) { const float4 u = coarseZ[a.y - nVC]; c.x += u.x; c.y += u.y; c.z += u.z; }
+	if (levels > 2) { const float4 u = coarseZ[a.z - nVC]; c.x += u.x; c.y += u.y; c.z += u.z; }
+	if (levels > 3) { const float4 u = coarseZ[a.w - nVC]; c.x += u.x; c.y += u.y; c.z += u.z; }
+	float4 y = z[ov];
+	y.x += c.x; y.y += c.y; y.z += c.z;
+	z[ov] = make_float4(y.x, y.y, y.z, 0.f);
+}
+
 }  // namespace
 
 #ifndef MAS_CPU_EMULATION   // host side: launches (the emulation has its own launcher)
@@ -592,7 +612,7 @@ int apply_begin(Context* c, const float4* r)
 
 // coarse levels: needs the complete level-1 residuals in coarseR (after the exchange when world > 1)
 // `capturing`: called from apply_forked (stream capture), where MAS_OPT_APPLY_CHAIN may fork the level-1 solves off the chain.
-static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false)
+static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bool skipProlongSum = false)
 {
 	if (c->numLevel < 2) return MAS_OK;
 	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
@@ -676,7 +696,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false)
 		c->applyLaunches += 1;
 	}
 	const int first = c->world > 1 ? c->l1Slice[c->rank] : 0, last = c->world > 1 ? c->l1Slice[c->rank + 1] : cnt1;
-	if (last > first)
+	if (last > first && !skipProlongSum)
 	{
 		prolong_sum_kernel<<<cdiv(last - first, 256), 256, 0, st>>>(c->coarseZ.p, c->goingNext.p, begin1, first, last, c->nVC,
 			prolonged_top(c) - 2, c->coarseZsum.p);
@@ -747,6 +767,9 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		return rc;
 	}
 	const int b0 = c->ownFineBegin, b1 = b0 + head, b2 = c->ownFineEnd;
+	// MAS_OPT_APPLY_CHAIN bit 2: the whole level-0 solve is in the head, so add_coarse is all that follows the chain and can
+	// walk the ancestors itself (no prolong_sum)
+	const bool walk = (c->optApplyChain & 4) && c->world == 1 && head == ownBanks;
 	MAS_CUDA(c, cudaEventRecord(c->evFork, st));
 	MAS_CUDA(c, cudaStreamWaitEvent(c->sideA, c->evFork, 0));
 	launch_fine(c, c->sideA, r, z, b0, b1, 0);                      // level-0 part only, no coarse data needed
@@ -755,7 +778,7 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		cudaStream_t saved = c->stream;
 		c->stream = st;
 		int rc = apply_begin(c, r);
-		if (rc == MAS_OK) rc = launch_coarse(c, st, true);
+		if (rc == MAS_OK) rc = launch_coarse(c, st, true, walk);
 		c->stream = saved;
 		if (rc != MAS_OK) return rc;
 	}
@@ -768,7 +791,11 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		const int vBegin = b0 * 32, vEnd = b1 * 32 < c->nv ? b1 * 32 : c->nv;
 		if (vEnd > vBegin)
 		{
-			add_coarse_kernel<<<cdiv(vEnd - vBegin, 256), 256, 0, st>>>(c->s2o.p, c->goingNext.p, c->coarseZsum.p, vBegin, vEnd, c->nVC, z);
+			if (walk)
+				add_coarse_walk_kernel<<<cdiv(vEnd - vBegin, 256), 256, 0, st>>>(c->s2o.p, c->coarseTables.p, c->coarseZ.p, vBegin, vEnd, c->nVC,
+					top - 1, z);
+			else
+				add_coarse_kernel<<<cdiv(vEnd - vBegin, 256), 256, 0, st>>>(c->s2o.p, c->goingNext.p, c->coarseZsum.p, vBegin, vEnd, c->nVC, z);
 			c->applyLaunches += 1;
 		}
 	}
@@ -795,7 +822,8 @@ int prioritize_apply_graph(Context* c, cudaGraph_t graph)
 		if (type != cudaGraphNodeTypeKernel) continue;
 		cudaKernelNodeParams kp;
 		MAS_CUDA(c, cudaGraphKernelNodeGetParams(nodes[i], &kp));
-		const bool streaming = kp.func == (void*)solve_fine_kernel || kp.func == (void*)add_coarse_kernel;
+		const bool streaming = kp.func == (void*)solve_fine_kernel || kp.func == (void*)add_coarse_kernel ||
+			kp.func == (void*)add_coarse_walk_kernel;
 		cudaKernelNodeAttrValue v;
 		v.priority = streaming ? prLow : prHigh;
 		MAS_CUDA(c, cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributePriority, &v));

@@ -3,7 +3,8 @@
 // launched in the order of apply_begin + apply_end for a single-GPU context.
 //   apply_emu < in.bin > out.bin
 //   in : int32 nv, numLevel, totalClusters, levelSize[(numLevel + 1) * 2]; int32 s2o[nv]; int32 goingNext[totalClusters];
-//        float32 dense inverses [totalClusters / 32][96][96]; float32 r[nv][4]
+//        float32 dense inverses [totalClusters / 32][96][96]; float32 r[nv][4]; int32 coarseTables[nv][4]
+//   env: MAS_EMU_TOP_FROM_L1 / MAS_EMU_WALK = the launch sequences of MAS_OPT_APPLY_CHAIN bits 1 / 2
 //   out: float32 z[nv][4]
 #include "cuda_emu.h"
 
@@ -41,11 +42,17 @@ int main()
 		}
 	}
 	const auto rIn = rd<float4>((size_t)nv);
+	const auto coarseTables = rd<int4>((size_t)nv);
+	const bool walk = getenv("MAS_EMU_WALK") != nullptr && L >= 2;    // head = all banks: level-0 solve first, coarse part added last
 	std::vector<float4> z((size_t)nv, make_float4(7.f, 7.f, 7.f, 7.f));
 	const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 	std::vector<float4> coarseR((size_t)(nCoarse > 0 ? nCoarse : 1), zero), coarseZ(coarseR), zsum(coarseR);
 	const int top = L < 4 ? L : 4;                     // prolonged_top() without MAS_OPT_PROLONG_ALL_LEVELS
 
+	if (walk)
+		emu::launch(cdiv(nFine, kWarpsPerCta), kApplyThreads, [&] {
+			solve_fine_kernel(packed.data(), rIn.data(), s2o.data(), goingNext.data(), zsum.data(), nv, nVC, 0, nFine, 0, 0, z.data());
+		});
 	if (L >= 2)
 	{
 		// apply_begin
@@ -81,10 +88,18 @@ int main()
 			emu::launch(nCoarseBlocks, 128, [&] {
 				solve_coarse_kernel(packed.data() + (size_t)nFine * kTri, coarseR.data(), coarseZ.data(), 0, nL1Blocks, nL1Blocks);
 			});
-		if (cnt1 > 0)
+		if (cnt1 > 0 && !walk)
 			emu::launch(cdiv(cnt1, 256), 256, [&] {
 				prolong_sum_kernel(coarseZ.data(), goingNext.data(), begin1, 0, cnt1, nVC, top - 2, zsum.data());
 			});
+	}
+	if (walk)
+	{
+		emu::launch(cdiv(nv, 256), 256, [&] {
+			add_coarse_walk_kernel(s2o.data(), coarseTables.data(), coarseZ.data(), 0, nv, nVC, top - 1, z.data());
+		});
+		fwrite(z.data(), sizeof(float4), z.size(), stdout);
+		return 0;
 	}
 	// apply_end
 	emu::launch(cdiv(nFine, kWarpsPerCta), kApplyThreads, [&] {

@@ -33,6 +33,7 @@ def _input(o, mesh, r):
              o.sorted_get_original().astype(np.int32), o.going_next()[:tc].astype(np.int32)]
     parts += [o.dense_inverse(b).astype(np.float32) for b in range(tc // 32)]
     parts.append(np.ascontiguousarray(r, np.float32))
+    parts.append(np.ascontiguousarray(o.coarse_tables(), np.int32))
     return b"".join(p.tobytes() for p in parts)
 
 
@@ -79,6 +80,18 @@ def test_emulated_apply_with_the_top_walk_starting_at_level_1(name, emulator, sy
     data = _input(o32, mesh, synth.residual(mesh.nv, 2))
     a = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True).stdout
     b = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True, env=dict(os.environ, MAS_EMU_TOP_FROM_L1="1")).stdout
+    assert a == b and len(a) == 16 * mesh.nv
+
+
+@pytest.mark.parametrize("name", ["cloth64_three_levels", "cloud900_two_levels_multi_bank_top", "cloth182_four_levels"])
+def test_emulated_apply_with_the_ancestor_walk(name, emulator, synth, oracle_lib):
+    """MAS_OPT_APPLY_CHAIN bit 2 (experimental): level-0 solve first, then the chain without prolong_sum, then add_coarse_walk
+    (every vertex adds Z_1 + Z_2 + ... of its own ancestors, in prolong_sum's order): bit-identical z."""
+    mesh = CASES[name](synth)
+    o32 = make_oracle(oracle_lib, mesh, "f")
+    data = _input(o32, mesh, synth.residual(mesh.nv, 2))
+    a = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True).stdout
+    b = subprocess.run([emulator], input=data, capture_output=True, timeout=900, check=True, env=dict(os.environ, MAS_EMU_WALK="1")).stdout
     assert a == b and len(a) == 16 * mesh.nv
 
 

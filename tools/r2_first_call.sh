@@ -14,7 +14,7 @@ tail -c 600 gpurun_out/r2_bench_1gpu.json | tee -a gpurun_out/r2_summary.txt
 timeout 200 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2_bench_reference.json 2>/dev/null
 for cfg in 0 1 2; do
   timeout 200 python bench.py --config $cfg --lean --steps 200 --warmup 10 > gpurun_out/r2_chain0_cfg$cfg.json 2>/dev/null
-  timeout 200 python bench.py --config $cfg --lean --steps 200 --warmup 10 --apply-chain 3 > gpurun_out/r2_chain1_cfg$cfg.json 2>/dev/null
+  timeout 200 python bench.py --config $cfg --lean --steps 200 --warmup 10 --apply-chain 7 > gpurun_out/r2_chain1_cfg$cfg.json 2>/dev/null
   python - <<PY | tee -a gpurun_out/r2_summary.txt
 import json
 a = json.loads(open("gpurun_out/r2_chain0_cfg$cfg.json").read().strip().splitlines()[-1]); b = json.loads(open("gpurun_out/r2_chain1_cfg$cfg.json").read().strip().splitlines()[-1])
