@@ -302,6 +302,7 @@ __global__ void copy_b_kernel(const float4* __restrict__ b, float4* __restrict__
 
 }  // namespace
 
+#ifndef MAS_CPU_EMULATION   // host side: launches (tests/emu/pcg_emu.cpp, test infrastructure, has its own launcher)
 int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges, const int* idx, const float4* b, float4* x,
 	float relTol, int maxIter, int usePrecond, int* itersOut, float* relResOut)
 {
@@ -410,5 +411,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	c->pcgConverged = host.done;
 	return MAS_OK;
 }
+
+#endif  // MAS_CPU_EMULATION
 
 }  // namespace mas

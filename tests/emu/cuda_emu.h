@@ -198,6 +198,8 @@ inline unsigned char* emu_dynamic_smem()
 	return buf;
 }
 inline void __threadfence_block() {}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline int __shfl_xor_sync(unsigned m, int v, int mask) { return __shfl_sync(m, v, (int)((emu::tid.x & 31) ^ (unsigned)mask)); }
 
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
