@@ -8,6 +8,11 @@ MAS_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_zz_limits.py -m g
 echo "experimental tests rc=$?" | tee -a gpurun_out/r2_summary.txt
 timeout 120 python tools/invert_variant_bench.py > gpurun_out/r2_invert_variants.json 2> gpurun_out/r2_invert_variants.err
 tail -1 gpurun_out/r2_invert_variants.json | tee -a gpurun_out/r2_summary.txt
+# 1b. ncu --set full of the inversion kernel, shipped and experimental (512^2: 8,192 blocks per launch; one launch each)
+for v in 0 1 4; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:fine_assemble_invert -s 2 -c 1 \
+    -o gpurun_out/r2_invert_v$v -f python tools/invert_variant_bench.py 512 $v > gpurun_out/r2_ncu_invert_v$v.log 2>&1
+done
 # 2. the bench line (now with both host stagings in e2e) and the reference arm
 timeout 400 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err
 tail -c 600 gpurun_out/r2_bench_1gpu.json | tee -a gpurun_out/r2_summary.txt
