@@ -144,7 +144,9 @@ enum
 	MAS_INT_PCG_CONVERGED = 12,    /* 1 if the last mas_pcg_solve met its tolerance */
 	MAS_INT_PEER_ERROR = 13,       /* 1 if a peer-memory wait ever timed out (a rank stopped publishing) */
 	MAS_INT_ALIGNED_CUTS = 14,     /* sharded contexts: 1 if no level-1 bank straddles a shard cut (the apply exchanges level-2 residuals) */
-	MAS_INT_HOST_PULL_CHOICE = 15  /* MAS_OPT_HOST_PULL = 2: -1 still sampling, 0 copy engine kept, 1 kernel pull kept */
+	MAS_INT_HOST_PULL_CHOICE = 15, /* MAS_OPT_HOST_PULL = 2: -1 still sampling, 0 copy engine kept, 1 kernel pull kept */
+	MAS_INT_HOST_BYTES_IN = 16,    /* bytes the last host-pointer mas_apply moved host -> device ... */
+	MAS_INT_HOST_BYTES_OUT = 17    /* ... and device -> host (a shard with page-locked buffers moves its own vertices only) */
 };
 
 /* mas_get_array keys: copies an internal device array to a HOST buffer (parity tests) */
@@ -227,6 +229,11 @@ int mas_peer_attach(mas_handle_t h, const void* handles, void* const* pointers);
  * usePreconditioner != 0.  Single-GPU contexts only. */
 int mas_pcg_solve(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const int* csrIdx,
 	const float* b, float* x, float relTol, int maxIter, int usePreconditioner, int mem, int* itersOut, float* relResOut);
+
+/* Waits for everything enqueued on the context's stream.  On a sharded context this is also where a failed peer exchange
+ * surfaces: if a device-side wait for another rank's coarse residuals ever timed out (~2 s; that rank died or never
+ * launched its apply) this call — and every later mas_apply — returns MAS_ERR_CUDA; the z of that apply is invalid. */
+int mas_synchronize(mas_handle_t h);
 
 /* introspection */
 int mas_get_int(mas_handle_t h, int key, long long* out);

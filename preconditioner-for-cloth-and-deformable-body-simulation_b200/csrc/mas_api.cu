@@ -67,6 +67,29 @@ __global__ void __launch_bounds__(256) pull_host_kernel(const float4* __restrict
 	}
 }
 
+// Sharded host-pointer apply: only the vertices this rank owns cross PCIe.  Owned vertices are a contiguous range in sorted
+// (Morton) order and scattered in the caller's order; consecutive sorted vertices are spatial neighbours, so their original
+// indices come in short runs and the 16-byte accesses of a warp merge into a few PCIe requests.  Four vertices per thread
+// in flight.  gather: dst[ov] = src[ov] (host -> staging);  the same kernel with the roles swapped returns z.
+__global__ void __launch_bounds__(256) copy_owned_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+	const int* __restrict__ s2o, int vBegin, int vEnd)
+{
+	const int stride = gridDim.x * blockDim.x;
+	for (int v0 = vBegin + blockIdx.x * blockDim.x + threadIdx.x; v0 < vEnd; v0 += 4 * stride)
+	{
+		int ov[4];
+		float4 val[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) ov[u] = v0 + u * stride < vEnd ? s2o[v0 + u * stride] : -1;
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (ov[u] >= 0) val[u] = src[ov[u]];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+			if (ov[u] >= 0) dst[ov[u]] = val[u];
+	}
+}
+
 // device-side address of a page-locked host buffer, or nullptr for pageable memory (which only the copy engine can read)
 static const float4* mapped_host_pointer(const void* host)
 {
@@ -136,10 +159,22 @@ static void close_peers(Context* c)
 	c->p2p = false;
 }
 
+// sticky: a peer wait of the sharded apply timed out at some point (a rank died or never launched); z is not to be trusted
+static int peer_failed(Context* c)
+{
+	if (c->peerErrHost && *reinterpret_cast<volatile unsigned*>(c->peerErrHost) != 0u)
+	{
+		c->err = "peer-memory exchange timed out: a rank stopped publishing its coarse residuals (results are invalid)";
+		return MAS_ERR_CUDA;
+	}
+	return MAS_OK;
+}
+
 static void free_all(Context* c)
 {
 	drop_graph(c);
 	close_peers(c);
+	if (c->peerErrHost) { cudaFreeHost(c->peerErrHost); c->peerErrHost = nullptr; c->peerErrDev = nullptr; }
 	unregister_host_ranges(c);
 	release(c->arena); release(c->cutInfo);
 	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
@@ -343,6 +378,12 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 		if (int rc = reserve(c, c->arena, bytes)) return rc;
 		MAS_CUDA(c, cudaMemsetAsync(c->arena.p, 0, bytes, c->stream));
 		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (!c->peerErrHost)
+		{
+			MAS_CUDA(c, cudaHostAlloc((void**)&c->peerErrHost, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+			*c->peerErrHost = 0u;
+			MAS_CUDA(c, cudaHostGetDevicePointer((void**)&c->peerErrDev, c->peerErrHost, 0));
+		}
 	}
 	c->hierarchyCached = false;
 	if (int rc = order_vertices(c, dPos, dStarts, dIdx)) return rc;
@@ -473,6 +514,7 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 	if (c->world > 1 && !c->p2p)
 		return fail(c, MAS_ERR_INVALID, "sharded context: attach the peers (mas_peer_attach) or use mas_apply_begin / exchange / mas_apply_end");
 	MAS_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = peer_failed(c)) return rc;        // sticky: an earlier apply lost a peer
 	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
 	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
@@ -481,6 +523,34 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 		register_host_range(c, residual, sizeof(float4) * (size_t)c->nv);
 		register_host_range(c, z, sizeof(float4) * (size_t)c->nv);
 	}
+	const size_t whole = sizeof(float4) * (size_t)c->nv;
+	if (c->world > 1)
+	{
+		// A shard reads r and writes z for ITS OWN vertices only; the caller's z entries of other ranks' vertices stay as they
+		// are.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / MAS_OPT_REGISTER_HOST): kernels move just the owned
+		// entries through the buffers' device mappings, 2 x 16 B per owned vertex over PCIe.  Pageable buffers can only be
+		// reached by the copy engine: whole r in, whole z in (to preserve the foreign entries), whole z out.
+		const int vBegin = c->ownFineBegin * 32 < c->nv ? c->ownFineBegin * 32 : c->nv;
+		const int vEnd = c->ownFineEnd * 32 < c->nv ? c->ownFineEnd * 32 : c->nv;
+		const size_t owned = sizeof(float4) * (size_t)(vEnd - vBegin);
+		const float4* mr = mapped_host_pointer(residual);
+		float4* mz = const_cast<float4*>(mapped_host_pointer(z));
+		int grid = cdiv(vEnd - vBegin, 4 * 256);
+		if (grid > 32 * c->smCount) grid = 32 * c->smCount;
+		if (grid < 1) grid = 1;
+		if (mr) copy_owned_kernel<<<grid, 256, 0, c->stream>>>(mr, c->rIn.p, c->s2o.p, vBegin, vEnd);
+		else MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, whole, cudaMemcpyHostToDevice, c->stream));
+		if (!mz) MAS_CUDA(c, cudaMemcpyAsync(c->zOut.p, z, whole, cudaMemcpyHostToDevice, c->stream));
+		if (int rc = run_apply_device(c, c->rIn.p, c->zOut.p)) return rc;
+		if (mz) copy_owned_kernel<<<grid, 256, 0, c->stream>>>(c->zOut.p, mz, c->s2o.p, vBegin, vEnd);
+		else MAS_CUDA(c, cudaMemcpyAsync(z, c->zOut.p, whole, cudaMemcpyDeviceToHost, c->stream));
+		MAS_CUDA(c, cudaGetLastError());
+		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->hostBytesIn = (long long)((mr ? owned : whole) + (mz ? 0 : whole));
+		c->hostBytesOut = (long long)(mz ? owned : whole);
+		return peer_failed(c);
+	}
+	c->hostBytesIn = c->hostBytesOut = (long long)whole;
 	const float4* mapped = c->optHostPull ? mapped_host_pointer(residual) : nullptr;
 	// auto mode (2): the first six applies with a page-locked residual time the two stagings (three each, the first of each
 	// is warm-up) with CUDA events on the stream; the faster one is kept for the rest of the context's life
@@ -521,7 +591,11 @@ int mas_apply_begin(mas_handle_t h, const float* residual, int mem)
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	c->applyLaunches = 0;
 	c->graphR = residual;
-	return apply_begin(c, (const float4*)residual);
+	// the caller sums the exchange buffer between _begin and _end: attached peers play no part in this protocol
+	c->phaseSplit = true;
+	const int rc = apply_begin(c, (const float4*)residual);
+	c->phaseSplit = false;
+	return rc;
 }
 
 int mas_apply_end(mas_handle_t h, float* z, int mem)
@@ -530,7 +604,10 @@ int mas_apply_end(mas_handle_t h, float* z, int mem)
 	Context* c = h;
 	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
 	MAS_CUDA(c, cudaSetDevice(c->device));
-	return apply_end(c, (const float4*)c->graphR, (float4*)z);
+	c->phaseSplit = true;
+	const int rc = apply_end(c, (const float4*)c->graphR, (float4*)z);
+	c->phaseSplit = false;
+	return rc;
 }
 
 int mas_pcg_solve(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const int* csrIdx,
@@ -659,16 +736,16 @@ int mas_get_int(mas_handle_t h, int key, long long* out)
 	case MAS_INT_PCG_CONVERGED: *out = c->pcgConverged; break;
 	case MAS_INT_ALIGNED_CUTS: *out = c->alignedCuts ? 1 : 0; break;
 	case MAS_INT_HOST_PULL_CHOICE: *out = c->pullChoice; break;
+	case MAS_INT_HOST_BYTES_IN: *out = c->hostBytesIn; break;
+	case MAS_INT_HOST_BYTES_OUT: *out = c->hostBytesOut; break;
 	case MAS_INT_PEER_ERROR:
 	{
 		*out = 0;
-		if (c->p2p)
+		if (c->peerErrHost)
 		{
-			unsigned v = 0;
-			const unsigned char* ctl = (const unsigned char*)c->arena.p + 2 * sizeof(float4) * c->arenaCap;
-			MAS_CUDA(c, cudaMemcpyAsync(&v, ctl + sizeof(unsigned) * (16 + 2), sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+			MAS_CUDA(c, cudaSetDevice(c->device));
 			MAS_CUDA(c, cudaStreamSynchronize(c->stream));
-			*out = v;
+			*out = *reinterpret_cast<volatile unsigned*>(c->peerErrHost);
 		}
 		break;
 	}
@@ -738,6 +815,15 @@ int mas_morton_encode(mas_handle_t h, const float* xyz, int count, uint64_t* cod
 	if (!h || !xyz || !codes_out || count <= 0) return MAS_ERR_INVALID;
 	MAS_CUDA(h, cudaSetDevice(h->device));
 	return morton_encode_points(h, xyz, count, (unsigned long long*)codes_out);
+}
+
+int mas_synchronize(mas_handle_t h)
+{
+	if (!h) return MAS_ERR_INVALID;
+	Context* c = h;
+	MAS_CUDA(c, cudaSetDevice(c->device));
+	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+	return peer_failed(c);
 }
 
 int mas_get_timing(mas_handle_t h, int which, float* ms_out)

@@ -267,7 +267,12 @@ __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int firs
 		// counters only grow; a peer that is already one apply ahead satisfies this too (its data sits in the other buffer)
 		while ((int)(ld_acquire_sys(f) - want) < 0)
 		{
-			if (clock64() - t0 > 4000000000ll) { ok = 0; atomicExch(pa.error, 1u); break; }   // ~2 s: a rank is gone
+			if (clock64() - t0 > 4000000000ll)   // ~2 s: a rank is gone.  Sticky flag in host memory: every later call fails.
+			{
+				ok = 0;
+				asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pa.error), "r"(1u) : "memory");
+				break;
+			}
 			__nanosleep(32);
 		}
 	}
@@ -571,7 +576,7 @@ static PeerArgs peer_args(const Context* c)
 	unsigned* ctl = reinterpret_cast<unsigned*>((unsigned char*)c->peerArena[c->rank] + 2 * sizeof(float4) * c->arenaCap);
 	pa.epoch = ctl + kMaxWorld;
 	pa.ticket = ctl + kMaxWorld + 1;
-	pa.error = ctl + kMaxWorld + 2;
+	pa.error = c->peerErrDev;      // page-locked host word: the host sees a timed-out wait without a device round trip
 	pa.cap = c->arenaCap;
 	pa.world = c->world;
 	pa.rank = c->rank;
@@ -583,16 +588,17 @@ int apply_begin(Context* c, const float4* r)
 	cudaStream_t st = c->stream;
 	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
 	if (c->numLevel < 2) return MAS_OK;
-	if (c->world > 1 && !c->p2p)
+	const bool peers = use_peers(c);
+	if (c->world > 1 && !peers)
 	{
 		MAS_CUDA(c, cudaMemsetAsync(c->coarseR.p, 0, sizeof(float4) * (size_t)c->nCoarseNodes, st));
 	}
 	const bool l2x = exchange_level2(c);
 	PeerArgs pa;
-	if (c->p2p) pa = peer_args(c);
+	if (peers) pa = peer_args(c);
 	if (ownBanks > 0)
 	{
-		const bool publish = c->p2p && !l2x;
+		const bool publish = peers && !l2x;
 		restrict_fine_kernel<<<cdiv(ownBanks, kWarpsPerCta * kRestrictBanks), kApplyThreads, 0, st>>>(r, c->s2o.p, c->goingNext.p, c->nv, c->nVC,
 			c->ownFineBegin, c->ownFineEnd, c->coarseR.p, publish ? pa.send[c->rank] : nullptr, publish ? pa.cap : 0ull,
 			publish ? pa.epoch : nullptr);
@@ -603,8 +609,8 @@ int apply_begin(Context* c, const float4* r)
 		// own level-1 banks -> level 2 (complete: no level-1 bank straddles a cut); published for the peers
 		const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
 		restrict_l1_kernel<<<cdiv(c->l1BlockEnd - c->l1BlockBegin, kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC,
-			c->l1BlockBegin, c->l1BlockEnd, c->coarseR.p, c->p2p ? pa.send[c->rank] : nullptr, c->p2p ? pa.cap : 0ull,
-			c->p2p ? pa.epoch : nullptr);
+			c->l1BlockBegin, c->l1BlockEnd, c->coarseR.p, peers ? pa.send[c->rank] : nullptr, peers ? pa.cap : 0ull,
+			peers ? pa.epoch : nullptr);
 		c->applyLaunches += 1;
 	}
 	return MAS_OK;
@@ -623,7 +629,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bo
 	// level-1 bank straddles a cut.  Their solve is forked off here and runs BESIDE restrict_l1 -> [peer exchange] ->
 	// restrict_top -> solve of the levels >= 2, instead of after them; the chain rejoins before prolong_sum.
 	const int ownL1Blocks = c->l1BlockEnd - c->l1BlockBegin;
-	const bool forkL1 = capturing && (c->optApplyChain & 1) && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (c->p2p && l2x));
+	const bool forkL1 = capturing && (c->optApplyChain & 1) && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (use_peers(c) && l2x));
 	if (forkL1)
 	{
 		MAS_CUDA(c, cudaEventRecord(c->evChainFork, st));
@@ -633,7 +639,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bo
 		c->applyLaunches += 1;
 		MAS_CUDA(c, cudaEventRecord(c->evChainL1, c->sideC));
 	}
-	if (c->p2p && !(l2x && c->numLevel < 3))
+	if (use_peers(c) && !(l2x && c->numLevel < 3))
 	{
 		const int first = l2x ? c->levelSize[2][1] - c->nVC : begin1 - c->nVC;
 		const int count = l2x ? c->levelSize[2][0] : cnt1;
@@ -746,7 +752,7 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 			// (optimum 6,500 banks).
 			const long long ownVerts = 32ll * ownBanks;
 			head = (int)(2400 + 8 * ownVerts / 2000);
-			if (c->p2p) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
+			if (use_peers(c)) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
 		}
 		// The CTA dispatcher works through grids in launch order, and stream / node priority does not let a later grid overtake
 		// the not-yet-dispatched CTAs of an earlier one (measured: beside a head of more than one wave, 148 x 8 CTAs, every

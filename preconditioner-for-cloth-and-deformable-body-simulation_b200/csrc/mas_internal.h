@@ -105,6 +105,7 @@ struct Context
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
 	struct HostRange { const void* p = nullptr; size_t bytes = 0; };
 	HostRange registered[4];     // ranges this context page-locked (and must unlock)
+	long long hostBytesIn = 0, hostBytesOut = 0;   // PCIe bytes of the last host-pointer apply (host -> device, device -> host)
 	int pullCalls = 0;           // auto mode: host-pointer applies sampled so far (3 per staging, the first of each is warm-up)
 	int pullChoice = -1;         // auto mode: -1 undecided, 0 copy engine, 1 kernel pull
 	float pullBestMs[2] = { 1e30f, 1e30f };
@@ -181,6 +182,9 @@ struct Context
 	void* peerArena[16] = {};         // arena base of every rank, peer-mapped; [rank] is the local one
 	bool peerOpened[16] = {};         // opened through cudaIpcOpenMemHandle (must be closed)
 	bool p2p = false;
+	bool phaseSplit = false;          // inside mas_apply_begin / mas_apply_end: the caller does the exchange, peers are ignored
+	unsigned* peerErrHost = nullptr;  // page-locked, device-mapped word: set by gather_peers when a peer wait times out (sticky)
+	unsigned* peerErrDev = nullptr;   // its device address
 
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
@@ -258,6 +262,7 @@ int apply_begin(Context* c, const float4* r);                                   
 int apply_end(Context* c, const float4* r, float4* z);                                            // mas_apply.cu
 int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st);                        // mas_apply.cu
 int prioritize_apply_graph(Context* c, cudaGraph_t graph);                                        // mas_apply.cu
+inline bool use_peers(const Context* c) { return c->p2p && !c->phaseSplit; }
 int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges, const int* idx, const float4* b, float4* x,
 	float relTol, int maxIter, int usePrecond, int* itersOut, float* relResOut);                  // mas_pcg.cu
 

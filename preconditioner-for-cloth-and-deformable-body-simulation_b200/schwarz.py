@@ -17,14 +17,14 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmas_b200.so")
+LIB_PATH = os.environ.get("MAS_B200_LIB") or os.path.join(_HERE, "libmas_b200.so")   # override: development builds only
 
 MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
 (OPT_PROLONG_ALL_LEVELS, OPT_APPLY_VARIANT, OPT_USE_GRAPH, OPT_TIME_KERNELS, OPT_ALIGN_CUTS, OPT_STENCIL_FIX,
  OPT_RESORT_PERIOD, OPT_HOST_PULL, OPT_INVERT_VARIANT, OPT_REGISTER_HOST, OPT_CACHE_HIERARCHY, OPT_APPLY_CHAIN) = range(12)
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
  INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
- INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS, INT_HOST_PULL_CHOICE) = range(16)
+ INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS, INT_HOST_PULL_CHOICE, INT_HOST_BYTES_IN, INT_HOST_BYTES_OUT) = range(18)
 (ARR_MORTON, ARR_SORTED_GET_ORIGINAL, ARR_ORIGINAL_GET_SORTED, ARR_GOING_NEXT, ARR_LEVEL_SIZE, ARR_FINE_CONNECT_MASK,
  ARR_COARSE_SPACE_TABLE, ARR_COARSE_TABLES, ARR_SORTED_ADJ_STARTS, ARR_SORTED_ADJ_IDX, ARR_STENCILS,
  ARR_STENCIL_INDEX_MAPPED, ARR_DENSE_INVERSE, ARR_MAPPED_R, ARR_MAPPED_Z, ARR_AABB) = range(16)
@@ -34,7 +34,7 @@ EXPORTS = [
     "mas_create", "mas_destroy", "mas_last_error", "mas_set_stream", "mas_set_option", "mas_set_partition",
     "mas_allocate", "mas_prepare", "mas_apply", "mas_prepare_begin", "mas_prepare_end", "mas_apply_begin",
     "mas_apply_end", "mas_exchange_buffer", "mas_get_int", "mas_get_array", "mas_morton_encode", "mas_get_timing",
-    "mas_pcg_solve", "mas_peer_export", "mas_peer_local", "mas_peer_attach",
+    "mas_pcg_solve", "mas_peer_export", "mas_peer_local", "mas_peer_attach", "mas_synchronize",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.mas_peer_export.argtypes = [vp, vp]
     lib.mas_peer_local.argtypes = [vp, C.POINTER(vp)]
     lib.mas_peer_attach.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.mas_synchronize.argtypes = [vp]
     lib.mas_pcg_solve.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_float, i, i, i, C.POINTER(i), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "mas_last_error":
@@ -145,6 +146,10 @@ class SeSchwarzPreconditioner:
         """stream: torch.cuda.Stream, raw cudaStream_t integer, or None for the default stream."""
         raw = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
         self._ck(self.lib.mas_set_stream(self.h, C.c_void_p(raw)))
+
+    def synchronize(self):
+        """Waits for the context's stream; raises if a peer exchange of a sharded apply ever timed out."""
+        self._ck(self.lib.mas_synchronize(self.h))
 
     def set_option(self, key: int, value: int):
         self._ck(self.lib.mas_set_option(self.h, key, value))

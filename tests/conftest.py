@@ -4,6 +4,11 @@ import sys
 
 import pytest
 
+# The in-process sharded tests run several contexts, each with its own apply-graph streams, that wait for each other ON THE
+# DEVICE: every one of them needs a hardware work queue of its own (the default of 8 makes streams share queues, and a
+# shard's publish can then sit behind another shard's spinning wait).  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
