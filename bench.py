@@ -264,10 +264,8 @@ def run_ours(args):
 
     if args.variant is not None:
         g.set_option(1, args.variant)
-    if args.apply_chain:
-        g.set_option(11, args.apply_chain)                         # experimental: level-1 solves forked off the coarse chain (MAS_OPT_APPLY_CHAIN)
     if args.invert_variant:
-        g.set_option(8, args.invert_variant)       # experimental inversion kernels (MAS_OPT_INVERT_VARIANT); default 0
+        g.set_option(8, args.invert_variant)       # MAS_OPT_INVERT_VARIANT: 0 tensor cores (default), 1 FP32 CUDA cores
     p2p = False
     if world > 1:
         drv = pkg.partition.ShardedSchwarzPreconditioner(g)
@@ -502,7 +500,7 @@ def run_ours(args):
                    "parallelism": (f"morton-sharded x{world}, " + ("peer-memory exchange fused into the restriction kernel (NVLink)"
                                                                       if p2p else "NCCL all-reduce of coarse residuals"))
                    if world > 1 else "single GPU"},
-        "setup_ms": setup_ms, "setup_device_ms": setup_device_ms, "invert_variant": args.invert_variant, "apply_chain": int(args.apply_chain),
+        "setup_ms": setup_ms, "setup_device_ms": setup_device_ms, "invert_variant": args.invert_variant,
         "e2e": {"value": units * e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv * world,
                 "d2h_bytes_per_step": 16 * nv * world, "steps": e2e_steps,
                 "staging": e2e_staging, "applies_per_s_by_staging": e2e_modes,
@@ -527,8 +525,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
     ap.add_argument("--variant", type=int, default=None, help="MAS_OPT_APPLY_VARIANT override (development sweeps)")
-    ap.add_argument("--apply-chain", type=int, default=0, help="MAS_OPT_APPLY_CHAIN bit mask (experimental apply graph shapes; 0 = shipped)")
-    ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT (experimental setup kernels; 0 = shipped)")
+    ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT: 0 = tcgen05 tensor cores (default), 1 = FP32 CUDA cores")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")
     args = ap.parse_args()

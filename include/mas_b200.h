@@ -98,32 +98,21 @@ enum
 	 * with a page-locked residual time both stagings on the device (three each), the faster one is kept
 	 * (mas_get_int(MAS_INT_HOST_PULL_CHOICE): -1 undecided, 0 copy engine, 1 kernel pull). */
 	MAS_OPT_HOST_PULL = 7,
-	/* EXPERIMENTAL, default 0; a bit mask.  Bit 0: the batched inversion factorises each 16x16 diagonal tile in registers,
-	 * redundantly on every warp of the CTA, instead of one warp walking it through shared memory (same operations in the
-	 * same order: bit-identical inverses).  Bit 1: the final product E^T D^-1 E runs on the tensor cores as 3xTF32
-	 * (hi/lo split, three m16n8k8 MMAs per product, FP32 accumulation), which holds the parity tolerance where plain TF32
-	 * does not.  Value 4: the whole blocked inversion on the tensor cores (panel products and trailing
-	 * updates as 3xTF32 MMAs too, the matrix held in accumulator fragments).  Takes effect at the next mas_prepare. */
+	/* Batched 96x96 inversion kernel.  0 (default): tcgen05 tensor cores — block Gauss-Jordan by 16-column panels, every
+	 * panel update one rank-16 GEMM with 3xTF32 operands (hi/lo split, FP32 accumulation in tensor memory), which holds the
+	 * parity tolerance where plain TF32 misses it by three orders of magnitude.  1: the FP32 CUDA-core
+	 * kernel (the reference's LDL^T elimination regrouped by 16x16 tiles).  Takes effect at the next mas_prepare. */
 	MAS_OPT_INVERT_VARIANT = 8,
 	/* Host-pointer mas_apply only, default 0.  1: a PAGEABLE residual / z buffer (std::vector, malloc) is page-locked where it
 	 * lies with cudaHostRegister the first time it is seen, so that every later copy runs at pinned-memory speed; up to
 	 * four ranges per context, unlocked by mas_destroy or by setting the option back to 0.  The caller must keep such a
 	 * buffer allocated until then (the reference's callers reuse r and z for the whole solve). */
 	MAS_OPT_REGISTER_HOST = 9,
-	/* Incremental setup, default 0.  1: a PreparePreconditioner without collision stencils that follows
-	 * another one without stencils keeps the clustering (levels, goingNext, coarse tables, shard cuts): it depends on the
-	 * sorted adjacency and the stencils only, so the rebuilt one would be identical bit for bit.  Assembly and inversion
-	 * always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds. */
-	MAS_OPT_CACHE_HIERARCHY = 10,
-	/* EXPERIMENTAL, default 0; a bit mask.  Bit 2: when the whole level-0 solve runs beside the coarse chain (small meshes),
-	 * the kernel that adds the coarse part afterwards walks each vertex's ancestors itself, as CollectFinalZ does (cpp:1698-1719),
-	 * and prolong_sum leaves the chain.  Bit 1: on small single-GPU meshes (at most 512 level-1 nodes) the one-CTA kernel
-	 * that restricts the top levels starts at level 1, one launch less on the latency-bound chain.  Bit 0: in the apply graph
-	 * the level-1 blocks (97 % of the coarse blocks; they need only the
-	 * level-1 residuals) are solved BESIDE restrict_l1 -> [peer exchange] -> restrict_top -> solve of the levels >= 2 instead
-	 * of after them (single-GPU contexts and sharded contexts with aligned cuts; hierarchies of three levels or more).
-	 * Same kernels, same arithmetic: bit-identical z. */
-	MAS_OPT_APPLY_CHAIN = 11
+	/* Incremental setup, default 1: a PreparePreconditioner without collision stencils that follows another
+	 * one without stencils keeps the clustering (levels, goingNext, coarse tables, shard cuts): it depends on the sorted
+	 * adjacency and the stencils only, so the rebuilt one would be identical bit for bit (verified on hardware).  Assembly
+	 * and inversion always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds.  0: always rebuild. */
+	MAS_OPT_CACHE_HIERARCHY = 10
 };
 
 /* mas_get_int keys */

@@ -187,7 +187,7 @@ static void free_all(Context* c)
 	release(c->scanTotal); release(c->coarseTables);
 	release(c->diagIn); release(c->offdiagIn); release(c->rangesIn); release(c->efIn); release(c->eeIn); release(c->vfIn);
 	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
-	release(c->coarseAcc); release(c->packedInv); release(c->posTab);
+	release(c->coarseAcc); release(c->packedInv); release(c->posTab); release(c->posTab96); release(c->invertErr);
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
 	release(c->pcgR); release(c->pcgZ); release(c->pcgP); release(c->pcgAp); release(c->pcgB); release(c->pcgX);
 	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);
@@ -225,14 +225,11 @@ int mas_create(mas_handle_t* out, int device)
 	cudaEventCreateWithFlags(&c->evHead, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evCoarse, cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&c->evTail, cudaEventDisableTiming);
-	cudaEventCreateWithFlags(&c->evChainFork, cudaEventDisableTiming);
-	cudaEventCreateWithFlags(&c->evChainL1, cudaEventDisableTiming);
 	{
 		int prLow = 0, prHigh = 0;
 		cudaDeviceGetStreamPriorityRange(&prLow, &prHigh);
 		cudaStreamCreateWithPriority(&c->sideA, cudaStreamNonBlocking, prLow);
 		cudaStreamCreateWithPriority(&c->sideB, cudaStreamNonBlocking, prLow);
-		cudaStreamCreateWithPriority(&c->sideC, cudaStreamNonBlocking, prHigh);
 	}
 	*out = c;
 	return MAS_OK;
@@ -256,9 +253,6 @@ int mas_destroy(mas_handle_t h)
 	if (h->evHead) cudaEventDestroy(h->evHead);
 	if (h->evCoarse) cudaEventDestroy(h->evCoarse);
 	if (h->evTail) cudaEventDestroy(h->evTail);
-	if (h->evChainFork) cudaEventDestroy(h->evChainFork);
-	if (h->evChainL1) cudaEventDestroy(h->evChainL1);
-	if (h->sideC) cudaStreamDestroy(h->sideC);
 	if (h->sideA) cudaStreamDestroy(h->sideA);
 	if (h->sideB) cudaStreamDestroy(h->sideB);
 	delete h;
@@ -285,15 +279,11 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_USE_GRAPH: h->optUseGraph = value ? 1 : 0; break;
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
-	case MAS_OPT_APPLY_CHAIN:
-		if (value < 0 || value > 7) return fail(h, MAS_ERR_INVALID, "MAS_OPT_APPLY_CHAIN is a mask of bits 0, 1 and 2");
-		h->optApplyChain = value;
-		break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:
-		if (value < 0 || value > 4) return fail(h, MAS_ERR_INVALID, "unknown inversion variant");
+		if (value < 0 || value > 1) return fail(h, MAS_ERR_INVALID, "MAS_OPT_INVERT_VARIANT takes 0 (tensor cores) or 1 (FP32 CUDA cores)");
 		h->optInvertVariant = value;
 		return MAS_OK;   // takes effect at the next mas_prepare
 	case MAS_OPT_REGISTER_HOST:
@@ -451,8 +441,11 @@ int mas_prepare_end(mas_handle_t h)
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	if (int rc = assemble_and_invert_end(c)) return rc;
 	MAS_CUDA(c, cudaEventRecord(c->evB, c->stream));
+	int invertErr = 0;
+	if (c->invertErr.p) MAS_CUDA(c, cudaMemcpyAsync(&invertErr, c->invertErr.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
 	cudaEventElapsedTime(&c->lastPrepareMs, c->evA, c->evB);
+	if (invertErr) return fail(c, MAS_ERR_CUDA, "tensor-core inversion: an MMA completion wait timed out (inverses are invalid)");
 	c->prepared = true;
 	return MAS_OK;
 }

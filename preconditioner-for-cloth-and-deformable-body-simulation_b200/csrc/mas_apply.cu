@@ -525,7 +525,7 @@ __global__ void add_coarse_kernel(const int* __restrict__ s2o, const int* __rest
 	z[ov] = make_float4(y.x, y.y, y.z, 0.f);
 }
 
-// MAS_OPT_APPLY_CHAIN bit 2 (experimental): the same addition without prolong_sum — every vertex walks its own ancestors
+// The same addition without prolong_sum — every vertex walks its own ancestors
 // (CollectFinalZ as the reference writes it, cpp:1698-1719, through the Int4 ancestor table) and adds Z_1 + Z_2 + ... in
 // prolong_sum's order, so the result is bit-identical while one launch leaves the latency-bound chain.  Used when the whole
 // level-0 solve fits in the head of the apply graph (small meshes), where this kernel is all that follows the chain.
@@ -617,28 +617,13 @@ int apply_begin(Context* c, const float4* r)
 }
 
 // coarse levels: needs the complete level-1 residuals in coarseR (after the exchange when world > 1)
-// `capturing`: called from apply_forked (stream capture), where MAS_OPT_APPLY_CHAIN may fork the level-1 solves off the chain.
-static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bool skipProlongSum = false)
+// skipProlongSum: the caller adds the coarse part with add_coarse_walk (which walks the ancestors itself)
+static int launch_coarse(Context* c, cudaStream_t st, bool skipProlongSum = false)
 {
 	if (c->numLevel < 2) return MAS_OK;
 	const int cnt1 = c->levelSize[1][0], begin1 = c->levelSize[1][1];
 	const int nCoarseBlocks = c->nCoarseNodes / 32;
 	const bool l2x = exchange_level2(c);
-	// MAS_OPT_APPLY_CHAIN (experimental): the level-1 blocks (97 % of the coarse blocks) need nothing but the level-1
-	// residuals, which are complete once restrict_fine has run — on a sharded context with aligned cuts as well, because no
-	// level-1 bank straddles a cut.  Their solve is forked off here and runs BESIDE restrict_l1 -> [peer exchange] ->
-	// restrict_top -> solve of the levels >= 2, instead of after them; the chain rejoins before prolong_sum.
-	const int ownL1Blocks = c->l1BlockEnd - c->l1BlockBegin;
-	const bool forkL1 = capturing && (c->optApplyChain & 1) && c->numLevel > 2 && ownL1Blocks > 0 && (c->world == 1 || (use_peers(c) && l2x));
-	if (forkL1)
-	{
-		MAS_CUDA(c, cudaEventRecord(c->evChainFork, st));
-		MAS_CUDA(c, cudaStreamWaitEvent(c->sideC, c->evChainFork, 0));
-		solve_coarse_kernel<<<ownL1Blocks, 128, 0, c->sideC>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri,
-			c->coarseR.p, c->coarseZ.p, c->l1BlockBegin, ownL1Blocks, c->nL1Blocks);
-		c->applyLaunches += 1;
-		MAS_CUDA(c, cudaEventRecord(c->evChainL1, c->sideC));
-	}
 	if (use_peers(c) && !(l2x && c->numLevel < 3))
 	{
 		const int first = l2x ? c->levelSize[2][1] - c->nVC : begin1 - c->nVC;
@@ -649,9 +634,10 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bo
 		gather_peers_kernel<<<grid, 256, 0, st>>>(peer_args(c), first, count, c->coarseR.p);
 		c->applyLaunches += 1;
 	}
-	// MAS_OPT_APPLY_CHAIN bit 1 (experimental): on small single-GPU meshes (at most 16 level-1 banks) the one-CTA kernel that
-	// walks the top levels starts at level 1 already, which takes restrict_l1 — one launch — off the latency-bound chain
-	const bool topFromL1 = (c->optApplyChain & 2) && c->world == 1 && c->numLevel > 2 && cnt1 <= 512;
+	// small single-GPU meshes (at most 16 level-1 banks): the one-CTA kernel that walks the top levels starts at level 1
+	// already, which takes restrict_l1 — one launch — off the latency-bound chain (bit-identical, measured on a B200:
+	// together with the ancestor walk below 12.5 -> 10.5 us per apply on the 64x64 cloth)
+	const bool topFromL1 = c->world == 1 && c->numLevel > 2 && cnt1 <= 512;
 	if (c->numLevel > 2 && !l2x && !topFromL1)
 	{
 		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, 0,
@@ -683,19 +669,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool capturing = false, bo
 	// redundantly on every rank, which removes any exchange of z
 	const int ownL1 = c->l1BlockEnd - c->l1BlockBegin;
 	const int solved = ownL1 + (nCoarseBlocks - c->nL1Blocks);
-	if (forkL1)
-	{
-		const int tops = nCoarseBlocks - c->nL1Blocks;
-		if (tops > 0)
-		{
-			// ownL1 = 0: block index = topBegin + blockIdx.x, the blocks of levels >= 2 only
-			solve_coarse_kernel<<<tops, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
-				c->coarseZ.p, c->l1BlockBegin, 0, c->nL1Blocks);
-			c->applyLaunches += 1;
-		}
-		MAS_CUDA(c, cudaStreamWaitEvent(st, c->evChainL1, 0));
-	}
-	else if (solved > 0)
+	if (solved > 0)
 	{
 		solve_coarse_kernel<<<solved, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
 			c->coarseZ.p, c->l1BlockBegin, ownL1, c->nL1Blocks);
@@ -773,9 +747,9 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		return rc;
 	}
 	const int b0 = c->ownFineBegin, b1 = b0 + head, b2 = c->ownFineEnd;
-	// MAS_OPT_APPLY_CHAIN bit 2: the whole level-0 solve is in the head, so add_coarse is all that follows the chain and can
-	// walk the ancestors itself (no prolong_sum)
-	const bool walk = (c->optApplyChain & 4) && c->world == 1 && head == ownBanks;
+	// small meshes: the whole level-0 solve is in the head, so add_coarse is all that follows the chain and walks the
+	// ancestors itself (no prolong_sum: one launch less on the chain)
+	const bool walk = c->world == 1 && head == ownBanks;
 	MAS_CUDA(c, cudaEventRecord(c->evFork, st));
 	MAS_CUDA(c, cudaStreamWaitEvent(c->sideA, c->evFork, 0));
 	launch_fine(c, c->sideA, r, z, b0, b1, 0);                      // level-0 part only, no coarse data needed
@@ -784,7 +758,7 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		cudaStream_t saved = c->stream;
 		c->stream = st;
 		int rc = apply_begin(c, r);
-		if (rc == MAS_OK) rc = launch_coarse(c, st, true, walk);
+		if (rc == MAS_OK) rc = launch_coarse(c, st, walk);
 		c->stream = saved;
 		if (rc != MAS_OK) return rc;
 	}

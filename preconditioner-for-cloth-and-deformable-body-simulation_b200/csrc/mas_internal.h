@@ -97,10 +97,9 @@ struct Context
 	int optAlignCuts = 1;
 	int optStencilFix = 0;       // read eeSets / vfSets from their own index 0 and form the third VF weight from b0 + b1 (Q2/Q3 fixed)
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
-	int optInvertVariant = 0;    // 1: register-resident diagonal-tile factorisation on every warp (experimental)
+	int optInvertVariant = 0;    // 0: tcgen05 tensor-core inversion (3xTF32 block Gauss-Jordan); 1: FP32 CUDA-core blocked LDL^T
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
-	int optApplyChain = 0;       // 1: apply graph solves the level-1 blocks beside the rest of the coarse chain (experimental)
-	int optCacheHierarchy = 0;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
+	int optCacheHierarchy = 1;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
 	bool hierarchyCached = false;   // the hierarchy in this context was built without stencils for the current ordering / options
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
 	struct HostRange { const void* p = nullptr; size_t bytes = 0; };
@@ -154,7 +153,9 @@ struct Context
 	DevBuf<double> coarseAcc;            // exchange buffer: [nCoarseBlocks][96*96] dense + [nCoarseNodes][9] carry
 	size_t coarseAccCount = 0;
 	DevBuf<float> packedInv;             // [nBlocks][kTri]
-	DevBuf<unsigned short> posTab;       // packed positions of the inversion kernel's register-tile outputs
+	DevBuf<unsigned short> posTab;       // packed positions of the CUDA-core inversion kernel's register-tile outputs
+	DevBuf<unsigned short> posTab96;     // tensor-core inversion kernel: packed position of (r, c), r >= c
+	DevBuf<int> invertErr;               // set by the tensor-core kernel if an MMA completion wait timed out
 
 	// ---- apply-time state
 	DevBuf<float4> coarseR, coarseZ, coarseZsum;  // indexed by node - nVC
@@ -205,8 +206,6 @@ struct Context
 	cudaEvent_t evF0 = nullptr, evF1 = nullptr;    // level-0 solve kernel (timed mode)
 	cudaEvent_t evS0 = nullptr, evS1 = nullptr;    // residual staging of the host-pointer apply (MAS_OPT_HOST_PULL = 2)
 	cudaStream_t sideA = nullptr, sideB = nullptr; // branches of the apply graph
-	cudaStream_t sideC = nullptr;                  // MAS_OPT_APPLY_CHAIN: level-1 solves beside the chain
-	cudaEvent_t evChainFork = nullptr, evChainL1 = nullptr;
 	cudaEvent_t evFork = nullptr, evHead = nullptr, evCoarse = nullptr, evTail = nullptr;
 	float lastApplyMs = 0.f, lastPrepareMs = 0.f;
 };

@@ -1,0 +1,298 @@
+// Batched 96x96 inversion on the Blackwell tensor cores (tcgen05.mma kind::tf32, accumulator in tensor memory): the default
+// setup path.  Included once by mas_assemble.cu inside namespace mas { namespace { ... } }, after PhaseClock.
+// Replaces LDLtInverse512 (SeSchwarzPreconditioner.cpp:1347-1546): same result within the parity bar, different algorithm.
+//
+// Algorithm: block Gauss-Jordan ("sweep") inversion of the symmetric positive definite system by panels of 16 columns.
+// With T = A at the start, panel K (columns 16K .. 16K+15), C = T[:, K] (96 x 16) and P = T[K, K]^-1 (16 x 16):
+//     T[i, j] -= (C P)[i, :] . C[j, :]            for i, j outside block K
+//     T[i, K]  = (C P)[i, :],   T[K, j] = (C P)[j, :]^T,   T[K, K] = -P
+// and after the six panels T = -A^-1.  T stays symmetric throughout, the swept blocks hold (minus) inverses of principal
+// submatrices and the others Schur complements, so no entry outgrows ||A|| or ||A^-1||; there is no separate E^T D^-1 E
+// product as in the reference's LDL^T route.  Everything a panel does to T is ONE rank-16 GEMM over the full 96 x 96 square,
+//     T += Aop . Bop^T,    Aop[i] = -(C P)[i],  Bop[j] = C[j]            (i, j outside K)
+//                          Aop[x] = P[x, :],    Bop[x] = -I[x, :]        (x in K; row and column block K of T zeroed first)
+// which is what the tensor core is for: M = 128 (96 used) x N = 96 x K = 16 per panel, accumulated in place in TMEM.
+//
+// Precision: kind::tf32 keeps 10 mantissa bits of each operand, which misses the parity bar by three orders of magnitude;
+// every operand is split into hi + lo TF32 halves and the three products lo*hi + hi*lo + hi*hi are accumulated in FP32
+// (3xTF32: six tcgen05.mma per panel), which is indistinguishable from FP32 arithmetic on the oracle's blocks at
+// k/m = 10 .. 1e5 (tools/sweep_inversion_study.py replays this file's algorithm in numpy).  The 16x16 pivot
+// inverses, the products C P and all bookkeeping stay FP32 on the CUDA cores.
+//
+// Mapping: one CTA of 128 threads per system, persistent over systems, FOUR CTAs per SM (each owns 128 of the SM's 512 TMEM
+// columns; one CTA's serial chain — TMEM load, pivot inverse, C P, operand store, MMA — is hidden behind the other three).
+// Thread r < 96 owns row r of T: TMEM lane r, read and written with the 32-lane x 32-bit shape, so the column panel C[r, :]
+// is one tcgen05.ld of 16 columns and (C P)[r, :] is thread-local.  Warp 3 has no rows: it inverts the pivot block in
+// registers (lanes = rows, shuffles broadcast the pivot row) while warps 0-2 zero row / column block K, and its lane 0 issues
+// the MMAs.  Operands are written to shared memory in the K-major no-swizzle core-matrix layout (mas_tcgen05.cuh).
+constexpr int kTcThreads = 128;
+constexpr int kTcCols = 128;            // TMEM columns per CTA (power of two >= 96); 4 CTAs x 128 = all 512 columns of an SM
+constexpr int kTcPs = 20;               // row stride of the 16x16 pivot scratch (16-byte aligned rows)
+
+struct TcOperands                       // 28 KB, K-major core-matrix layout, rows 96..127 of A stay zero
+{
+	float aHi[128 * 16], aLo[128 * 16], bHi[96 * 16], bLo[96 * 16];
+};
+struct TcSmem
+{
+	union
+	{
+		alignas(128) float A[kDof * kLdP];      // the assembled system, row stride 97 (assembly; read once into TMEM)
+		TcOperands op;                          // panel operands (elimination)
+		float packed[kTri];                     // packed inverse (epilogue)
+	};
+	alignas(16) float piv[16 * kTcPs];          // pivot block T[K, K]
+	alignas(16) float P[16 * kTcPs];            // its inverse
+	float ownDiag[kBank][9];                    // assembly only, as in InvSmem
+	double folded[kBank][9];
+	int parent[kBank];
+	float fold[kBank][9];
+	alignas(8) uint64_t bar;                    // mbarrier: completion of a panel's MMAs
+	uint32_t tmemBase;
+};
+
+// In-place un-pivoted Gauss-Jordan inverse of the 16x16 pivot block, one warp.  Lanes l and l + 16 hold the two halves
+// (8 columns each) of row l & 15; step p broadcasts row p and the pivot with shuffles, every row subtracts its multiple.
+//   d = 1 / M[p][p];   row p: M[p][j] *= d, M[p][p] = d;   row i != p: M[i][j] -= M[i][p] d M[p][j], M[i][p] = -M[i][p] d
+__device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, float* __restrict__ P, const int lane)
+{
+	constexpr unsigned kAll = 0xffffffffu;
+	const int row = lane & 15, half = lane >> 4, c0 = 8 * half;
+	float m[8];
+	{
+		const float4 a = *reinterpret_cast<const float4*>(piv + row * kTcPs + c0), b = *reinterpret_cast<const float4*>(piv + row * kTcPs + c0 + 4);
+		m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+	}
+#pragma unroll
+	for (int p = 0; p < 16; ++p)
+	{
+		const int ph = p >> 3, pc = p & 7;                                 // half and register holding column p
+		const float pivot = __shfl_sync(kAll, m[pc], p + 16 * ph);          // M[p][p]
+		const float mine = __shfl_sync(kAll, m[pc], row + 16 * ph);         // M[row][p]
+		float prow[8];
+#pragma unroll
+		for (int c = 0; c < 8; ++c) prow[c] = __shfl_sync(kAll, m[c], p + 16 * half);   // M[p][my columns]
+		const float d = __frcp_rn(pivot);
+		if (row == p)
+		{
+#pragma unroll
+			for (int c = 0; c < 8; ++c) m[c] = __fmul_rn(prow[c], d);
+			if (half == ph) m[pc] = d;
+		}
+		else
+		{
+			const float g = __fmul_rn(mine, d);
+#pragma unroll
+			for (int c = 0; c < 8; ++c) m[c] = __fmaf_rn(-g, prow[c], m[c]);
+			if (half == ph) m[pc] = -g;
+		}
+	}
+	*reinterpret_cast<float4*>(P + row * kTcPs + c0) = make_float4(m[0], m[1], m[2], m[3]);
+	*reinterpret_cast<float4*>(P + row * kTcPs + c0 + 4) = make_float4(m[4], m[5], m[6], m[7]);
+}
+
+// one operand row (16 k) of thread / row `r`: hi and lo halves, four 16-byte stores each
+__device__ __forceinline__ void store_operand_row(float* __restrict__ hiBuf, float* __restrict__ loBuf, const int r, const float (&v)[16])
+{
+	float hi[16], lo[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) tc::split_tf32(v[k], hi[k], lo[k]);
+	unsigned char* h = reinterpret_cast<unsigned char*>(hiBuf) + tc::operand_offset(r, 0);
+	unsigned char* l = reinterpret_cast<unsigned char*>(loBuf) + tc::operand_offset(r, 0);
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	{
+		*reinterpret_cast<float4*>(h + q * tc::kLbo) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+		*reinterpret_cast<float4*>(l + q * tc::kLbo) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+	}
+}
+
+// In: s.A holds the assembled 96x96 system (row stride kLdP), all threads past the barrier that completed it.
+// Out: s.packed holds the packed inverse (lane-slot layout, mas_internal.h), all threads past a barrier.
+// pos96[r * 96 + c], r >= c: packed position of symmetric element (r, c).  `parity`: phase of s.bar, carried across systems.
+__device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uint32_t& parity, const unsigned short* __restrict__ pos96,
+	int* __restrict__ errFlag, PhaseClock& pc)
+{
+	const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+	const uint32_t myRow = tc::tmem_at(tb, 32 * warp, 0);       // TMEM address of this thread's row (the hardware adds the lane)
+
+	// padding nodes: zero (0,0) entry of the diagonal block -> identity (cpp:1365-1368)
+	if (t < kBank && s.A[tile_at(3 * t, 3 * t)] == 0.0f)
+	{
+		for (int i = 0; i < 3; ++i)
+			for (int j = 0; j < 3; ++j) s.A[tile_at(3 * t + i, 3 * t + j)] = (i == j) ? 1.0f : 0.0f;
+	}
+	__syncthreads();
+
+	// the system into tensor memory: thread r stores row r (conflict-free reads at the odd row stride)
+	if (warp < 3)
+	{
+#pragma unroll
+		for (int c0 = 0; c0 < kDof; c0 += 16)
+		{
+			float v[16];
+#pragma unroll
+			for (int j = 0; j < 16; ++j) v[j] = s.A[tile_at(t, c0 + j)];
+			tc::tmem_st16(myRow + c0, v);
+		}
+		tc::tmem_wait_st();
+	}
+	tc::fence_before_sync();
+	__syncthreads();                    // the tile array becomes the operand buffers
+	tc::fence_after_sync();
+	if (warp == 3)
+	{
+		// rows 96..127 of the A operand (M = 128 for the instruction, 96 rows of payload) are zero
+		float4* zh = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s.op.aHi) + tc::operand_bytes(96));
+		float4* zl = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(s.op.aLo) + tc::operand_bytes(96));
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			zh[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+			zl[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+	}
+	pc.mark(3);
+
+#pragma unroll 1
+	for (int K = 0; K < 6; ++K)
+	{
+		if (K > 0)
+		{
+			if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+			parity ^= 1u;
+			tc::fence_after_sync();
+		}
+		pc.mark(4);
+		float c[16];
+		if (warp < 3)
+		{
+			tc::tmem_ld16(myRow + 16 * K, c);              // C[r, :], and for the rows of block K the pivot block itself
+			if ((t >> 4) == K)
+			{
+				float4* dst = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
+#pragma unroll
+				for (int q = 0; q < 4; ++q) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+			}
+		}
+		__syncthreads();
+		pc.mark(5);
+		if (warp == 3)
+			invert16_warp(s.piv, s.P, lane);
+		else
+		{
+			// row and column block K of T are REPLACED by this panel: zero them, the GEMM then deposits the new values
+			const float zero[16] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+			tc::tmem_st16(myRow + 16 * K, zero);
+			if (warp == (K >> 1))
+			{
+				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb, 16 * K, 0));
+				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb, 16 * K, 64));
+			}
+			tc::tmem_wait_st();
+		}
+		__syncthreads();
+		pc.mark(6);
+		if (warp < 3)
+		{
+			float a[16];
+			if ((t >> 4) == K)
+			{
+				// rows of block K: Aop = P[x, :], Bop = -I[x, :]
+				const float4* src = reinterpret_cast<const float4*>(s.P + (t & 15) * kTcPs);
+#pragma unroll
+				for (int q = 0; q < 4; ++q)
+				{
+					const float4 v = src[q];
+					a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+				}
+#pragma unroll
+				for (int k = 0; k < 16; ++k) c[k] = (k == (t & 15)) ? -1.0f : 0.0f;
+			}
+			else
+			{
+				// Aop = -(C P)[r, :], Bop = C[r, :]
+#pragma unroll
+				for (int k = 0; k < 16; ++k) a[k] = 0.0f;
+#pragma unroll
+				for (int j = 0; j < 16; ++j)
+				{
+					const float4* prow = reinterpret_cast<const float4*>(s.P + j * kTcPs);
+					const float cj = -c[j];
+#pragma unroll
+					for (int q = 0; q < 4; ++q)
+					{
+						const float4 v = prow[q];
+						a[4 * q] = __fmaf_rn(cj, v.x, a[4 * q]);
+						a[4 * q + 1] = __fmaf_rn(cj, v.y, a[4 * q + 1]);
+						a[4 * q + 2] = __fmaf_rn(cj, v.z, a[4 * q + 2]);
+						a[4 * q + 3] = __fmaf_rn(cj, v.w, a[4 * q + 3]);
+					}
+				}
+			}
+			store_operand_row(s.op.aHi, s.op.aLo, t, a);
+			store_operand_row(s.op.bHi, s.op.bLo, t, c);
+		}
+		tc::fence_async_smem();
+		tc::fence_before_sync();
+		__syncthreads();
+		pc.mark(7);
+		if (t == 96)
+		{
+			tc::fence_after_sync();
+			constexpr uint32_t id = tc::idesc_tf32(128, 96);
+			const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
+#pragma unroll
+			for (int ks = 0; ks < 2; ++ks)
+			{
+				const uint32_t off = ks * 2 * tc::kLbo;
+				tc::mma_tf32(tb, tc::smem_desc(aL + off, tc::kLbo, tc::kSbo), tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), id, 1u);   // small terms first
+				tc::mma_tf32(tb, tc::smem_desc(aH + off, tc::kLbo, tc::kSbo), tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), id, 1u);
+				tc::mma_tf32(tb, tc::smem_desc(aH + off, tc::kLbo, tc::kSbo), tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), id, 1u);
+			}
+			tc::mma_commit(&s.bar);
+		}
+	}
+	if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+	parity ^= 1u;
+	tc::fence_after_sync();
+	pc.mark(8);
+
+	// T = -A^-1: lower triangle into the packed ("lane-slot") order
+	if (warp < 3)
+	{
+#pragma unroll 1
+		for (int c0 = 0; c0 <= 32 * warp + 16; c0 += 16)          // warp-uniform bound: columns up to the warp's last row
+		{
+			float v[16];
+			tc::tmem_ld16(myRow + c0, v);
+#pragma unroll
+			for (int j = 0; j < 16; ++j)
+				if (c0 + j <= t) s.packed[pos96[t * kDof + c0 + j]] = -v[j];
+		}
+	}
+	tc::fence_before_sync();
+	__syncthreads();
+	pc.mark(9);
+}
+
+// per-CTA set-up and tear-down of the tensor-memory allocation and the mbarrier
+__device__ __forceinline__ uint32_t tc_begin(TcSmem& s)
+{
+	if (threadIdx.x < 32) tc::tmem_alloc<kTcCols>(&s.tmemBase);
+	if (threadIdx.x == 32)
+	{
+		tc::mbar_init(&s.bar, 1);
+		tc::mbar_init_fence();
+	}
+	tc::fence_before_sync();
+	__syncthreads();
+	tc::fence_after_sync();
+	return s.tmemBase;
+}
+__device__ __forceinline__ void tc_end(const uint32_t tb)
+{
+	tc::fence_before_sync();
+	__syncthreads();
+	if (threadIdx.x < 32) tc::tmem_dealloc<kTcCols>(tb);
+}

@@ -4,7 +4,7 @@
 //   apply_emu < in.bin > out.bin
 //   in : int32 nv, numLevel, totalClusters, levelSize[(numLevel + 1) * 2]; int32 s2o[nv]; int32 goingNext[totalClusters];
 //        float32 dense inverses [totalClusters / 32][96][96]; float32 r[nv][4]; int32 coarseTables[nv][4]
-//   env: MAS_EMU_TOP_FROM_L1 / MAS_EMU_WALK = the launch sequences of MAS_OPT_APPLY_CHAIN bits 1 / 2
+//   env: MAS_EMU_TOP_FROM_L1 / MAS_EMU_WALK = the launch sequences apply_forked uses on small meshes
 //   out: float32 z[nv][4]
 #include "cuda_emu.h"
 
@@ -62,7 +62,7 @@ int main()
 		// launch_coarse
 		const int cnt1 = ls[2], begin1 = ls[3];
 		const int nCoarseBlocks = nCoarse / 32, nL1Blocks = pad32(cnt1) / 32;
-		const bool topFromL1 = getenv("MAS_EMU_TOP_FROM_L1") && L > 2 && cnt1 <= 512;     // MAS_OPT_APPLY_CHAIN bit 1
+		const bool topFromL1 = getenv("MAS_EMU_TOP_FROM_L1") && L > 2 && cnt1 <= 512;     // small meshes
 		if (L > 2 && !topFromL1)
 			emu::launch(cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, [&] {
 				restrict_l1_kernel(goingNext.data(), begin1, cnt1, nVC, 0, cdiv(cnt1, 32), coarseR.data(), nullptr, 0ull, nullptr);

@@ -89,7 +89,7 @@ int main()
 
 	// assemble_and_invert_begin
 	if (L > 1) emu::launch(cdiv(nVC, 256), 256, [&] { cross_bank_kernel(fa, 0, nVC); });
-	emu::launch(nFine, kInvThreads, [&] { fine_assemble_invert_kernel<0>(fa); });
+	emu::launch(nFine, kInvThreads, [&] { fine_assemble_invert_kernel(fa); });
 	// assemble_and_invert_end
 	for (int level = 1; level + 1 < L; ++level)
 	{
@@ -101,7 +101,7 @@ int main()
 	{
 		const int nL1Blocks = pad32(ls[2]) / 32;
 		emu::launch(nCoarseBlocks, kInvThreads, [&] {
-			coarse_invert_kernel<0>(dense, carry, packed.data() + (size_t)nFine * kTri, posTab.data(), 0, nL1Blocks, nL1Blocks);
+			coarse_invert_kernel(dense, carry, packed.data() + (size_t)nFine * kTri, posTab.data(), 0, nL1Blocks, nL1Blocks);
 		});
 	}
 	std::vector<float> out((size_t)kDof * kDof);

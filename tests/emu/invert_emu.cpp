@@ -1,8 +1,9 @@
-// TEST INFRASTRUCTURE ONLY.  Runs the batched 96x96 inversion of csrc/mas_invert.cuh — the very text the CUDA kernels
-// compile — on the CPU (tests/emu/cuda_emu.h) for every MAS_OPT_INVERT_VARIANT, on matrices read from stdin, and writes
-// the unpacked inverses to stdout.
-//   invert_emu <variant> < in.bin > out.bin      in: int32 count, then count x 96 x 96 float32 (row-major, symmetric)
-//                                                out: count x 96 x 96 float32
+// TEST INFRASTRUCTURE ONLY.  Runs the FP32 CUDA-core inversion of csrc/mas_invert.cuh (MAS_OPT_INVERT_VARIANT = 1) — the very
+// text the CUDA kernel compiles — on the CPU (tests/emu/cuda_emu.h), on matrices read from stdin, and writes the unpacked
+// inverses to stdout.  (The default tensor-core kernel, mas_invert_tc.cuh, needs tcgen05 hardware; its algorithm is replayed
+// in numpy by tools/sweep_inversion_study.py.)
+//   invert_emu < in.bin > out.bin      in: int32 count, then count x 96 x 96 float32 (row-major, symmetric)
+//                                      out: count x 96 x 96 float32
 #include "cuda_emu.h"
 
 #include <cstddef>
@@ -21,13 +22,11 @@ struct PhaseClock
 };
 #include "../../preconditioner-for-cloth-and-deformable-body-simulation_b200/csrc/mas_invert.cuh"
 
-template <int V>
 void invert_one(const float* dense, float* out)
 {
-	std::vector<unsigned char> smem(sizeof(InvSmem) + sizeof(float) * kTri + 64);
+	std::vector<unsigned char> smem(sizeof(InvSmem) + 64);
 	unsigned char* base = smem.data() + ((16 - (reinterpret_cast<uintptr_t>(smem.data()) & 15)) & 15);
 	InvSmem& s = *reinterpret_cast<InvSmem*>(base);
-	float* stage = reinterpret_cast<float*>(base + sizeof(InvSmem));
 	for (int r = 0; r < kDof; ++r)
 		for (int c = 0; c < kDof; ++c) s.A[tile_at(r, c)] = dense[r * kDof + c];
 	// the table ensure_pos_table() builds on the host (csrc/mas_assemble.cu)
@@ -44,7 +43,7 @@ void invert_one(const float* dense, float* out)
 	std::vector<float> packed(kTri);
 	emu::run(kInvThreads, [&] {
 		PhaseClock pc;
-		const float* p = invert_tile<V>(s, posTab.data(), pc, stage);
+		const float* p = invert_tile(s, posTab.data(), pc);
 		store_packed(p, packed.data());
 	});
 	for (int r = 0; r < kDof; ++r)
@@ -55,7 +54,7 @@ void invert_one(const float* dense, float* out)
 
 int main(int argc, char** argv)
 {
-	const int variant = argc > 1 ? atoi(argv[1]) : 0;
+	(void)argc; (void)argv;
 	int count = 0;
 	if (fread(&count, 4, 1, stdin) != 1 || count < 0 || count > 4096) return 2;
 	std::vector<float> in((size_t)count * 96 * 96), out((size_t)count * 96 * 96);
@@ -64,15 +63,7 @@ int main(int argc, char** argv)
 	{
 		const float* src = in.data() + (size_t)b * 9216;
 		float* dst = out.data() + (size_t)b * 9216;
-		switch (variant)
-		{
-		case 0: mas::invert_one<0>(src, dst); break;
-		case 1: mas::invert_one<1>(src, dst); break;
-		case 2: mas::invert_one<2>(src, dst); break;
-		case 3: mas::invert_one<3>(src, dst); break;
-		case 4: mas::invert_one<4>(src, dst); break;
-		default: return 3;
-		}
+		mas::invert_one(src, dst);
 	}
 	fwrite(out.data(), 4, out.size(), stdout);
 	return 0;

@@ -72,9 +72,9 @@ def test_emulated_apply_matches_the_oracle(name, emulator, synth, oracle_lib):
 
 @pytest.mark.parametrize("name", ["cloth50_ragged", "rippled64_fragmented"])
 def test_emulated_apply_with_the_top_walk_starting_at_level_1(name, emulator, synth, oracle_lib):
-    """MAS_OPT_APPLY_CHAIN bit 1 (experimental): restrict_top takes over from level 1 on small meshes instead of restrict_l1;
-    same sums over the same groups, so z is bit-identical to the shipped launch sequence (rippled64 has 554 level-1 nodes:
-    over the limit, the option must change nothing)."""
+    """Small single-GPU meshes (at most 512 level-1 nodes): restrict_top takes over from level 1 instead of restrict_l1; same
+    sums over the same groups, so z is bit-identical to the general launch sequence (rippled64 has 554 level-1 nodes: over the
+    limit, nothing changes)."""
     mesh = CASES[name](synth)
     o32 = make_oracle(oracle_lib, mesh, "f")
     data = _input(o32, mesh, synth.residual(mesh.nv, 2))
@@ -85,8 +85,8 @@ def test_emulated_apply_with_the_top_walk_starting_at_level_1(name, emulator, sy
 
 @pytest.mark.parametrize("name", ["cloth50_ragged", "cloud900_two_levels_multi_bank_top", "stacked2x24_ties"])
 def test_emulated_apply_with_the_ancestor_walk(name, emulator, synth, oracle_lib):
-    """MAS_OPT_APPLY_CHAIN bit 2 (experimental): level-0 solve first, then the chain without prolong_sum, then add_coarse_walk
-    (every vertex adds Z_1 + Z_2 + ... of its own ancestors, in prolong_sum's order): bit-identical z."""
+    """Meshes whose whole level-0 solve runs beside the coarse chain: level-0 solve first, then the chain without prolong_sum,
+    then add_coarse_walk (every vertex adds Z_1 + Z_2 + ... of its own ancestors, in prolong_sum's order): bit-identical z."""
     mesh = CASES[name](synth)
     o32 = make_oracle(oracle_lib, mesh, "f")
     data = _input(o32, mesh, synth.residual(mesh.nv, 2))

@@ -140,46 +140,35 @@ def test_host_pull_staging_is_bit_identical(gpu_cls, synth):
 import os  # noqa: E402
 
 
-@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="experimental kernels: set MAS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("name", ["cloth64", "cloth96_stiff", "tet16x16x8", "cloth96_collisions"])
-def test_experimental_invert_variant_is_bit_identical(name, gpu_cls, synth):
-    """MAS_OPT_INVERT_VARIANT bit 0 (register-resident diagonal-tile factorisation on every warp) performs the reference's
-    operations in the reference's order, like the shipped variant: every packed inverse must match bit for bit."""
-    def coll():
-        m = synth.cloth(96, with_topology=True)
-        return synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
-    mesh = {"cloth64": lambda: synth.cloth(64), "cloth96_stiff": lambda: synth.cloth(96, k=1e5),
-            "tet16x16x8": lambda: synth.tet_cube(16, 16, 8), "cloth96_collisions": coll}[name]()
-    a = gpu_cls(0).setup_from_mesh(mesh)
-    b = gpu_cls(0)
-    b.set_option(8, 1)
-    b.setup_from_mesh(mesh)
-    nb = a.num_blocks
-    fine = (mesh.nv + 31) // 32
-    # collision terms reach the coarse blocks through FP64 atomics (order-dependent, Q7): compare those by tolerance
-    for blk in sorted(set(list(range(0, nb, max(1, nb // 40))) + list(range(max(0, nb - 8), nb)))):
-        ia, ib = a.dense_inverse(blk), b.dense_inverse(blk)
-        if blk < fine or mesh.ef_total + mesh.ee_total + mesh.vf_total == 0:
-            assert np.array_equal(ia, ib), blk
-        else:
-            assert np.abs(ia - ib).max() <= 1e-5 * np.abs(ia).max(), blk
-
-
-@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="experimental kernels: set MAS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("name", ["cloth64", "cloth96_collisions", "tet16x16x8", "cloth200_stiff", "chain100_fragmented_banks"])
-def test_experimental_tensor_core_product_holds_the_parity_bar(name, variant, gpu_cls, synth, oracle_lib):
-    """MAS_OPT_INVERT_VARIANT bit 1: E^T D^-1 E as 3xTF32 MMAs; value 4: the whole blocked inversion on the tensor cores.
-    Not bit-identical to the FP32 kernel, but they have to pass the very same parity test (structure bit-exact, inverses
-    and z within the FP64-arbitrated bars)."""
+def test_cuda_core_inversion_holds_the_parity_bar(name, gpu_cls, synth, oracle_lib):
+    """MAS_OPT_INVERT_VARIANT = 1: the FP32 CUDA-core inversion (the reference's elimination regrouped by tiles) instead of the
+    default tensor-core kernel.  Both have to pass the very same parity test (structure bit-exact, inverses and z within the
+    FP64-arbitrated bars); every other GPU test runs the tensor-core default."""
     def with_variant(device):
         g = gpu_cls(device)
-        g.set_option(8, variant)
+        g.set_option(8, 1)
         return g
     _structure_and_apply(name, with_variant, synth, oracle_lib)
 
 
-@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="unmeasured option: set MAS_EXPERIMENTAL=1")
+def test_inversion_kernels_agree_on_every_block(gpu_cls, synth):
+    """Tensor-core (3xTF32 block Gauss-Jordan) against CUDA-core (FP32 LDL^T) inverses of the same setup, every block of a
+    stiff cloth with collisions: two different algorithms, each within rounding of the true inverse."""
+    m = synth.cloth(96, k=1e4, with_topology=True)
+    mesh = synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
+    a = gpu_cls(0).setup_from_mesh(mesh)
+    b = gpu_cls(0)
+    b.set_option(8, 1)
+    b.setup_from_mesh(mesh)
+    worst = 0.0
+    for blk in range(a.num_blocks):
+        ia, ib = a.dense_inverse(blk), b.dense_inverse(blk)
+        assert np.array_equal(ia, ia.T)
+        worst = max(worst, float(np.abs(ia - ib).max() / np.abs(ib).max()))
+    assert worst < 2e-5, worst
+
+
 def test_register_host_option_keeps_results(gpu_cls, synth):
     """MAS_OPT_REGISTER_HOST page-locks the caller's pageable r / z where they lie; results are unchanged, with and without
     the kernel pull, and the ranges are released when the option is cleared."""
@@ -203,9 +192,8 @@ def test_register_host_option_keeps_results(gpu_cls, synth):
     assert np.array_equal(z, z0)
 
 
-@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="unmeasured option: set MAS_EXPERIMENTAL=1")
 def test_cached_hierarchy_gives_identical_setup(gpu_cls, synth):
-    """MAS_OPT_CACHE_HIERARCHY: collision-free prepares keep the clustering; a prepare with stencils rebuilds it."""
+    """MAS_OPT_CACHE_HIERARCHY (default on): collision-free prepares keep the clustering; a prepare with stencils rebuilds it."""
     m = synth.cloth(96, with_topology=True)
     coll = synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
     stiff = synth.cloth(96, k=5000.0)
@@ -226,27 +214,25 @@ def test_cached_hierarchy_gives_identical_setup(gpu_cls, synth):
     a, b = run(0), run(1)
     for k, ((ga, la, za, na), (gb, lb, zb, nb)) in enumerate(zip(a, b)):
         assert np.array_equal(ga, gb) and np.array_equal(la, lb)
-        if k != 1:                                  # collision atomics make that setup order-dependent (Q7)
-            assert np.array_equal(za, zb)
+        # the coarse Galerkin sums are FP64 atomics (order-dependent in the last bit, Q7): z agrees to rounding, not bit for bit
+        assert np.abs(za - zb).max() <= 1e-6 * np.abs(za).max()
     assert b[0][3] < a[0][3] and b[3][3] < a[3][3]  # fewer launches when the clustering is kept
     assert b[2][3] == a[2][3]                       # first collision-free prepare after one with stencils rebuilds
 
 
-@pytest.mark.skipif(not os.environ.get("MAS_EXPERIMENTAL"), reason="unmeasured option: set MAS_EXPERIMENTAL=1")
-@pytest.mark.parametrize("mask", [1, 2, 4, 7])
 @pytest.mark.parametrize("n", [64, 192, 512])
-def test_apply_chain_fork_is_bit_identical(n, mask, gpu_cls, synth):
-    """MAS_OPT_APPLY_CHAIN: bit 0 = the level-1 solves run beside the rest of the coarse chain in the apply graph, bit 1 = the
-    one-CTA top walk starts at level 1 on small meshes, bit 2 = add_coarse walks the ancestors itself (no prolong_sum); same kernels on the same data, so z must not change by a bit (graph
-    path = device pointers)."""
+def test_graph_and_plain_launch_sequences_agree_bit_for_bit(n, gpu_cls, synth):
+    """The captured apply graph (two branches; on small meshes the shortened coarse chain: top walk from level 1, ancestor walk
+    instead of prolong_sum) against the strictly sequential un-captured launches: same arithmetic in the same order, so z must
+    not differ by a bit."""
     import torch
     mesh = synth.cloth(n)
     g = gpu_cls(0).setup_from_mesh(mesh, device_inputs=True)
     r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
     z0, z1 = torch.empty_like(r), torch.empty_like(r)
     g.Preconditioning(z0, r)
-    g.set_option(11, mask)
-    for _ in range(3):
-        g.Preconditioning(z1, r)
+    g.set_option(2, 0)                    # MAS_OPT_USE_GRAPH = 0
+    g.set_option(1, 0)                    # MAS_OPT_APPLY_VARIANT = 0: no concurrent head
+    g.Preconditioning(z1, r)
     torch.cuda.synchronize()
     assert torch.equal(z0, z1)
