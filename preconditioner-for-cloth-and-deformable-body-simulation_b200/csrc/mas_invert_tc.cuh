@@ -54,6 +54,14 @@ struct TcSmem
 // In-place un-pivoted Gauss-Jordan inverse of the 16x16 pivot block, one warp.  Lanes l and l + 16 hold the two halves
 // (8 columns each) of row l & 15; step p broadcasts row p and the pivot with shuffles, every row subtracts its multiple.
 //   d = 1 / M[p][p];   row p: M[p][j] *= d, M[p][p] = d;   row i != p: M[i][j] -= M[i][p] d M[p][j], M[i][p] = -M[i][p] d
+// The sixteen steps are one dependent chain (shuffle -> reciprocal -> multiply -> FMA), the serial part of every panel: no
+// divergent branches (the pivot row is the same FMA with base 0 and factor -d) and a two-instruction reciprocal.
+__device__ __forceinline__ float rcp_newton(const float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
+}
 __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, float* __restrict__ P, const int lane)
 {
 	constexpr unsigned kAll = 0xffffffffu;
@@ -72,20 +80,12 @@ __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, flo
 		float prow[8];
 #pragma unroll
 		for (int c = 0; c < 8; ++c) prow[c] = __shfl_sync(kAll, m[c], p + 16 * half);   // M[p][my columns]
-		const float d = __frcp_rn(pivot);
-		if (row == p)
-		{
+		const float d = rcp_newton(pivot);
+		const bool isP = row == p;
+		const float g = isP ? -d : __fmul_rn(mine, d);
 #pragma unroll
-			for (int c = 0; c < 8; ++c) m[c] = __fmul_rn(prow[c], d);
-			if (half == ph) m[pc] = d;
-		}
-		else
-		{
-			const float g = __fmul_rn(mine, d);
-#pragma unroll
-			for (int c = 0; c < 8; ++c) m[c] = __fmaf_rn(-g, prow[c], m[c]);
-			if (half == ph) m[pc] = -g;
-		}
+		for (int c = 0; c < 8; ++c) m[c] = __fmaf_rn(-g, prow[c], isP ? 0.0f : m[c]);
+		if (half == ph) m[pc] = -g;                                         // d for the pivot row, -M[row][p] d elsewhere
 	}
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0) = make_float4(m[0], m[1], m[2], m[3]);
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0 + 4) = make_float4(m[4], m[5], m[6], m[7]);
@@ -189,6 +189,16 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb, 16 * K, 0));
 				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb, 16 * K, 64));
 			}
+			// the B operand does not need P: Bop = C[r, :], and -I[x, :] for the rows of block K
+			if ((t >> 4) == K)
+			{
+				float e[16];
+#pragma unroll
+				for (int k = 0; k < 16; ++k) e[k] = (k == (t & 15)) ? -1.0f : 0.0f;
+				store_operand_row(s.op.bHi, s.op.bLo, t, e);
+			}
+			else
+				store_operand_row(s.op.bHi, s.op.bLo, t, c);
 			tc::tmem_wait_st();
 		}
 		__syncthreads();
@@ -198,7 +208,7 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 			float a[16];
 			if ((t >> 4) == K)
 			{
-				// rows of block K: Aop = P[x, :], Bop = -I[x, :]
+				// rows of block K: Aop = P[x, :]
 				const float4* src = reinterpret_cast<const float4*>(s.P + (t & 15) * kTcPs);
 #pragma unroll
 				for (int q = 0; q < 4; ++q)
@@ -206,12 +216,10 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 					const float4 v = src[q];
 					a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
 				}
-#pragma unroll
-				for (int k = 0; k < 16; ++k) c[k] = (k == (t & 15)) ? -1.0f : 0.0f;
 			}
 			else
 			{
-				// Aop = -(C P)[r, :], Bop = C[r, :]
+				// Aop = -(C P)[r, :]
 #pragma unroll
 				for (int k = 0; k < 16; ++k) a[k] = 0.0f;
 #pragma unroll
@@ -231,7 +239,6 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 				}
 			}
 			store_operand_row(s.op.aHi, s.op.aLo, t, a);
-			store_operand_row(s.op.bHi, s.op.bLo, t, c);
 		}
 		tc::fence_async_smem();
 		tc::fence_before_sync();
@@ -265,10 +272,12 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 		for (int c0 = 0; c0 <= 32 * warp + 16; c0 += 16)          // warp-uniform bound: columns up to the warp's last row
 		{
 			float v[16];
+			const uint4 p0 = *reinterpret_cast<const uint4*>(pos96 + t * kDof + c0), p1 = *reinterpret_cast<const uint4*>(pos96 + t * kDof + c0 + 8);
+			const unsigned pw[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };      // sixteen 16-bit positions
 			tc::tmem_ld16(myRow + c0, v);
 #pragma unroll
 			for (int j = 0; j < 16; ++j)
-				if (c0 + j <= t) s.packed[pos96[t * kDof + c0 + j]] = -v[j];
+				if (c0 + j <= t) s.packed[(pw[j >> 1] >> (16 * (j & 1))) & 0xffffu] = -v[j];
 		}
 	}
 	tc::fence_before_sync();

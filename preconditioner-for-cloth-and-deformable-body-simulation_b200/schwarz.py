@@ -115,6 +115,7 @@ class SeSchwarzPreconditioner:
         if rc != 0:
             raise MasError(f"mas_create(device={device}) failed with {rc}: no usable sm_100 GPU (no CPU fallback)")
         self.device = device
+        self.invert_variant = 0          # MAS_OPT_INVERT_VARIANT: 0 tensor cores (default), 1 FP32 CUDA cores
         self.rank, self.world = rank, world
         if world > 1:
             self._ck(self.lib.mas_set_partition(self.h, rank, world))
@@ -153,6 +154,8 @@ class SeSchwarzPreconditioner:
 
     def set_option(self, key: int, value: int):
         self._ck(self.lib.mas_set_option(self.h, key, value))
+        if key == OPT_INVERT_VARIANT:
+            self.invert_variant = value
 
     # ---- the reference's three calls
     def AllocatePrecoditioner(self, numVerts: int, numEdges: int, numFaces: int):  # noqa: N802 (reference spelling)

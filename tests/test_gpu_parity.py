@@ -76,6 +76,13 @@ def test_structure_and_apply_vs_oracle(name, gpu_cls, synth, oracle_lib):
     os_, oi = o32.sorted_adjacency()
     assert np.array_equal(gs, os_) and np.array_equal(gi, oi)
 
+    # Stated tolerances.  FP32 CUDA-core inversion (MAS_OPT_INVERT_VARIANT = 1, round-to-nearest FMAs like the reference):
+    # inverses within 4x, z within 2x of the FP32 reference arithmetic's own distance from FP64.  Tensor-core inversion
+    # (default): 8x for both — tcgen05 accumulators TRUNCATE (round toward zero) where an FMA rounds to nearest, a one-sided
+    # error that shows on ill-conditioned blocks (measured worst case: the 32-vertex chain, 4.4x; numpy replay with a
+    # truncating accumulator in tools/sweep_inversion_study.py).  PCG iteration counts are identical (tests/test_gpu_pcg.py).
+    tensor = getattr(g, "invert_variant", 0) == 0
+    inv_slack, z_slack = (8.0, 8.0) if tensor else (4.0, 2.0)
     # dense inverses of a spread of blocks over every level
     nb = g.num_blocks
     assert nb == o32.total_clusters // 32
@@ -86,7 +93,7 @@ def test_structure_and_apply_vs_oracle(name, gpu_cls, synth, oracle_lib):
         scale = np.abs(oi_).max()
         e_gpu = np.abs(gi_ - oi_).max() / scale
         e_ref = np.abs(o32i - oi_).max() / scale
-        assert e_gpu <= 4 * e_ref + 1e-5, (b, e_gpu, e_ref)
+        assert e_gpu <= inv_slack * e_ref + 1e-5, (b, e_gpu, e_ref)
         assert np.array_equal(gi_, gi_.T)
         worst = max(worst, e_gpu)
 
@@ -96,16 +103,16 @@ def test_structure_and_apply_vs_oracle(name, gpu_cls, synth, oracle_lib):
         g.Preconditioning(z, r, 3 * mesh.nv)
         assert np.all(z[:, 3] == 0.0)                     # w = 0 on output (cpp:1687)
         z32, z64 = o32.apply(r), o64.apply(r)
-        ok, e_gpu, e_ref = arbiter_ok(z, z32, z64)
+        ok, e_gpu, e_ref = arbiter_ok(z, z32, z64, slack=z_slack)
         assert ok, f"{name}: |gpu-f64|={e_gpu:.3e} vs |fp32 oracle-f64|={e_ref:.3e}"
-        assert rel_l2(z, z32) <= 3 * e_ref + 1e-5
+        assert rel_l2(z, z32) <= (z_slack + 1) * e_ref + 1e-5
         # coarse residual / solution hierarchy (levels >= 1)
         nVC = (mesh.nv + 31) // 32 * 32
         R, Z = g.mapped_r()[nVC:, :3], g.mapped_z()[nVC:, :3]
         if R.size:
             Ro, Zo = o64.mapped_r()[nVC:], o64.mapped_z()[nVC:]
             assert np.abs(R - Ro).max() <= 1e-5 * max(1.0, np.abs(Ro).max())
-            assert rel_l2(Z, Zo) <= 3 * e_ref + 1e-4
+            assert rel_l2(Z, Zo) <= (z_slack + 1) * e_ref + 1e-4
 
 
 def test_device_pointers_match_host_pointers(gpu_cls, synth):
