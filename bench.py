@@ -40,6 +40,39 @@ WORKLOADS = {0: "cloth 64x64 (4,096 verts)", 1: "cloth 512x512 (262,144 verts) +
              3: "tet cube 128x128x64 (1,048,576 verts)", 4: "cloth 2048x2048 (4,194,304 verts), 5 levels"}
 
 
+def weak_grid(world: int):
+    """(a, b): the weak-scaling cloth is 1024a x 1024b vertices with a * b = world."""
+    b = 1
+    while (b * 2) * (b * 2) <= world and world % (b * 2) == 0:
+        b *= 2
+    return world // b, b
+
+
+def workload_and_config(args, world: int):
+    """`config` of the JSON line: identical for both arms (the driver compares them), so only what is known before anything
+    runs.  Returns (config dict, units = 1M-vertex applies per whole-mesh apply, nv)."""
+    weak = world > 1 and args.scaling == "weak" and args.config == 2
+    workload = WORKLOADS[args.config]
+    nv = {0: 4096, 1: 262144, 2: 1048576, 3: 1048576, 4: 4194304}[args.config]
+    units = 1.0
+    if weak:
+        a, b = weak_grid(world)
+        nv = 1048576 * world
+        units = float(world)
+        workload = (f"cloth {1024 * a}x{1024 * b} ({nv:,} verts = {world} x 1,048,576), 8-neighbour springs, Morton-sharded over "
+                    f"{world} GPUs; the reference arm (one host, no GPUs) times ONE 1,048,576-vertex unit on all host threads")
+    elif world > 1:
+        workload += f", Morton-sharded over {world} GPUs (strong scaling); the reference arm times the same mesh on the host"
+    cfg = {"workload": workload, "nv": nv,
+           "units": (f"value = {units:g} x whole-mesh applies/s: one apply of the sharded {nv:,}-vertex mesh counts as {units:g} applies of "
+                     f"the 1M-vertex cloth (per-GPU work fixed)") if weak else "whole-mesh applies/s",
+           "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step per GPU vs 126 MB L2 (the CPU arm streams the "
+                 "same 630 MB per 1M vertices from host memory)",
+           "timing": "ours: CUDA events on the launching stream, max over ranks; reference: host wall clock, mean over steps",
+           "parallelism": f"morton-sharded x{world}" if world > 1 else "single GPU"}
+    return cfg, units, nv
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -109,6 +142,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_peak_tflops():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops"])
+    except Exception:
+        return 1680.0          # this pool's measured dense bf16 figure (B200_PROFILING.md fallback)
+
+
 def traffic_from_profile():
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if present."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -152,6 +193,7 @@ def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
         p.apply(r, out=z)
         best = min(best, time.perf_counter() - t0)
     mean = (time.perf_counter() - t_all) / steps
+    cpu_reference_apply.last_z = z          # the reference's z on this (mesh, r): value parity is checked against it
     return 1.0 / mean, 1.0 / best, setup_ms, kind
 
 
@@ -177,25 +219,26 @@ def cpu_reference_pcg(mesh, b, threads: int):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     pkg = importlib.import_module(PKG_NAME)
-    mesh = pkg.synth.config(args.config)
+    cfg, units, _ = workload_and_config(args, max(world, args.gpus))
+    mesh = pkg.synth.config(args.config)      # the CPU arm times one unit (the BASELINE mesh) on all host threads
     r = pkg.synth.residual(mesh.nv)
     threads = host_threads()
-    steps = max(1, min(args.steps, 40))        # bounded: 40 applies of the 1M mesh is ~2 s of CPU work after setup
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
     t0 = time.perf_counter()
-    mean_rate, best_rate, setup_ms, kind = cpu_reference_apply(mesh, r, steps, min(args.warmup, 3), threads)
+    mean_rate, best_rate, setup_ms, kind = cpu_reference_apply(mesh, r, steps, warmup, threads)
     out = {
         "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "applies/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / mean_rate, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / mean_rate, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "nv": mesh.nv, "timing": "host wall clock, mean over steps",
-                   "units": "1M-vertex applies/s; with --gpus N (weak scaling) the GPU arm shards N such units, the CPU arm times one "
-                            "unit on all host threads (its throughput per unit does not depend on the mesh size)"},
+        "config": cfg,
         "setup_ms": setup_ms,
         "cpu_baseline": {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
-                         "sample": f"whole mesh, {steps} applies after 1 setup + warm-up; best single apply {1e3 / best_rate:.2f} ms"},
+                         "sample": f"whole {WORKLOADS[args.config]} mesh, {steps} applies after 1 setup + {warmup} warm-up applies; "
+                                   f"best single apply {1e3 / best_rate:.2f} ms"},
         "e2e": {"value": mean_rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
@@ -223,23 +266,17 @@ def run_ours(args):
     S = pkg.synth
     dev = f"cuda:{local}"
     weak = world > 1 and args.scaling == "weak" and args.config == 2
-    workload = WORKLOADS[args.config]
+    cfg, units, _ = workload_and_config(args, world)
     if args.config == 2:
         # generated on the device (bit-identical to the numpy recipe, tests/test_synth.py): no multi-GB host pass per rank
-        b = 1
-        while weak and (b * 2) * (b * 2) <= world and world % (b * 2) == 0:
-            b *= 2
-        a = world // b if weak else 1
+        a, b = weak_grid(world) if weak else (1, 1)
         mesh = S.cloth_rect_device(1024 * a, 1024 * b, torch.device(dev))
-        if weak:
-            workload = (f"cloth {1024 * a}x{1024 * b} ({mesh.nv:,} verts = {world} x 1,048,576), 8-neighbour springs, "
-                        f"Morton-sharded over {world} GPUs")
     elif args.config == 4:
         mesh = S.cloth_rect_device(2048, 2048, torch.device(dev))      # strong scaling: the 4.2M-vertex cloth split N ways
     else:
         mesh = S.config(args.config)
     nv = mesh.nv
-    units = nv / 1048576.0 if weak else 1.0      # 1M-vertex applies per whole-mesh apply
+    assert nv == cfg["nv"]
 
     stream = torch.cuda.current_stream()
     g = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=stream)
@@ -253,14 +290,15 @@ def run_ours(args):
     d_in = (t(mesh.diag), t(mesh.offdiag), t(mesh.nbr_starts), tb(mesh.ef) if mesh.ef.size else None,
             tb(mesh.ee) if mesh.ee.size else None, tb(mesh.vf) if mesh.vf.size else None)
 
-    def prepare():
-        if world == 1:
-            g.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total, mesh.vf_total)
+    def prepare(eng=None):
+        eng = eng or g
+        if eng.world == 1:
+            eng.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total, mesh.vf_total)
         else:
-            g.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total,
-                                    mesh.vf_total, phase="begin")
-            dist.all_reduce(g.exchange_tensor(0))
-            g.prepare_end()
+            eng.PreparePreconditioner(d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], mesh.ef_total, mesh.ee_total,
+                                      mesh.vf_total, phase="begin")
+            dist.all_reduce(eng.exchange_tensor(0))
+            eng.prepare_end()
 
     if args.variant is not None:
         g.set_option(1, args.variant)
@@ -282,6 +320,18 @@ def run_ours(args):
         setup_wall.append((time.perf_counter() - t0) * 1e3)
     setup_ms = min(setup_wall)
     setup_device_ms = g.timing_ms(0) if world == 1 else None
+    # the same setup with the clustering rebuilt every time (MAS_OPT_CACHE_HIERARCHY = 0): what a first prepare, or one with
+    # new collision stencils, costs
+    setup_full_ms = None
+    if world == 1 and not args.lean:
+        g.set_option(10, 0)
+        acc = []
+        for _ in range(3):
+            prepare()
+            acc.append(g.timing_ms(0))
+        setup_full_ms = min(acc)
+        g.set_option(10, 1)
+        prepare()
 
     r = t(S.residual(nv))
     z = torch.zeros_like(r)
@@ -300,14 +350,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
-    # keep the GPU busy long enough for at least a few clock samples: repeat the timed block, keep the best
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -332,34 +382,82 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = g.apply_launches
 
+    # ---- sharded runs: the timed z is checked in the run.  (1) no device-side peer wait timed out on any rank (that would
+    # leave stale coarse residuals behind: mas_synchronize raises); (2) the shards merge to the z a single GPU computes for the
+    # same mesh and r ("G-GPU z equals 1-GPU z"; only the summation order of the FP64 coarse accumulators differs).
+    parity = None
+    if world > 1:
+        g.synchronize()
+        peer_err = torch.tensor([g.peer_error], device=dev, dtype=torch.int32)
+        dist.all_reduce(peer_err, op=dist.ReduceOp.MAX)
+        b0, b1 = g.owned_fine_blocks
+        s2o = torch.from_numpy(g.sorted_get_original().astype(np.int64)).to(dev)
+        own = s2o[min(32 * b0, nv):min(32 * b1, nv)]
+        merged = torch.zeros_like(z)
+        merged[own] = z[own]
+        covered = torch.zeros(nv, device=dev, dtype=torch.int32)
+        covered[own] = 1
+        dist.all_reduce(merged)
+        dist.all_reduce(covered)
+        parity = {"peer_error": int(peer_err.item()), "every_vertex_owned_once": bool((covered == 1).all().item())}
+        if rank == 0:
+            one = pkg.SeSchwarzPreconditioner(device=local, stream=stream)
+            one.m_positions, one.m_edges, one.m_faces, one.m_neighbours = g.m_positions, g.m_edges, g.m_faces, g.m_neighbours
+            if args.invert_variant:
+                one.set_option(8, args.invert_variant)
+            one.AllocatePrecoditioner(nv, mesh.ne, mesh.nf)
+            prepare(one)
+            z1 = torch.empty_like(r)
+            one.Preconditioning(z1, r)
+            torch.cuda.synchronize()
+            rel = float((merged - z1)[:, :3].double().norm() / z1[:, :3].double().norm())
+            parity.update({"rel_l2_sharded_vs_single_gpu": rel, "tolerance": 1e-5, "ok": bool(rel < 1e-5 and parity["peer_error"] == 0
+                                                                                               and parity["every_vertex_owned_once"])})
+            one.close()
+            del z1
+        del merged, covered
+
     # ---- e2e: public host-pointer API, pinned host buffers, H2D + apply + D2H inside the timed region
-    r_h = torch.from_numpy(S.residual(nv)).pin_memory()
+    r_np = S.residual(nv)
+    r_h = torch.from_numpy(r_np).pin_memory()
     z_h = torch.zeros_like(r_h).pin_memory()
     r_stage, z_stage = torch.empty_like(r), torch.empty_like(r)
 
-    def e2e_step():
+    def e2e_step(zb=None, rb=None):
+        zb, rb = (z_h if zb is None else zb), (r_h if rb is None else rb)
         if world == 1 or p2p:
-            g.Preconditioning(z_h, r_h)          # mas_apply(MAS_MEM_HOST): cudaMemcpyAsync in, graph, cudaMemcpyAsync out, sync
+            g.Preconditioning(zb, rb)            # mas_apply(MAS_MEM_HOST): host r in, apply graph, host z out, synchronous
         else:
-            r_stage.copy_(r_h, non_blocking=True)
+            r_stage.copy_(rb, non_blocking=True)
             g.apply_begin(r_stage)
             dist.all_reduce(exch)
             g.apply_end(z_stage)
-            z_h.copy_(z_stage, non_blocking=True)
+            zb.copy_(z_stage, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    def time_e2e(n, zb=None, rb=None, warm=3):
+        for _ in range(warm):
+            e2e_step(zb, rb)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            e2e_step(zb, rb)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return 1.0 / float(dt.item())
+
     e2e_steps = 1 if args.lean else max(5, min(args.steps, 50))
-    for _ in range(0 if args.lean else 3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+    e2e_rate = time_e2e(e2e_steps, warm=0 if args.lean else 3)
+    if world == 1 or p2p:
+        h2d, d2h = g.get_int(16), g.get_int(17)            # counted by the library from the copies it issued
+    else:
+        h2d = d2h = 16 * nv
     if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_rate = 1.0 / float(e2e_s.item())
+        moved = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+        dist.all_reduce(moved)
+        h2d, d2h = int(moved[0].item()), int(moved[1].item())
 
     # ---- dominant kernel alone, CUDA events on the launching stream (inside the library), un-captured launches
     fine_ms = None
@@ -409,14 +507,27 @@ def run_ours(args):
     if fine_ms:
         fine_bytes = algorithmic_bytes(n_fine, nv)
         achieved = fine_bytes / (fine_ms * 1e-3) / 1e9
+        # setup: bytes that have to move (Hessian blocks and indices in, packed inverses out) and the tensor-core work of the
+        # inversion (six rank-16 updates of 128 x 96 per system, three TF32 products each)
+        nnz = int(mesh.nbr_starts[-1])
+        setup_bytes = n_blocks * 4656 * 4 + nv * (36 + 16 + 8) + nnz * (36 + 4)
+        setup_flop = n_blocks * 6 * 3 * 2 * 128 * 96 * 16
+        tf32_peak = measured_peak_tflops() / 2.0
         roof = {"bound": "hbm", "kernel": "solve_fine_kernel (level-0 SchwarzLocalXSym fused with gather/prolongation)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": fine_bytes, "kernel_ms_mean": fine_ms, "kernel_ms_median": fine_ms_med,
                 "traffic": traffic_from_profile(),
+                "traffic_source": "profiles/roofline_traffic.json (ncu --set full of this kernel, dram__bytes_read + dram__bytes_write; not re-measured in this run)",
                 "whole_apply": {"algorithmic_bytes": algorithmic_bytes(n_blocks, nv),
                                 "achieved": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 1e9,
                                 "frac": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 1e9 / peak,
-                                "frac_of_8TBs": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 8e12}}
+                                "frac_of_8TBs": algorithmic_bytes(n_blocks, nv) / (ms_per_step * 1e-3) / 8e12},
+                "setup": {"ms": setup_device_ms, "bytes_bound": setup_bytes, "hbm_gbs": setup_bytes / (setup_device_ms * 1e-3) / 1e9,
+                          "hbm_frac": setup_bytes / (setup_device_ms * 1e-3) / 1e9 / peak,
+                          "tensor_flop": setup_flop, "tensor_tflops": setup_flop / (setup_device_ms * 1e-3) / 1e12,
+                          "tensor_peak_tf32_tflops": tf32_peak, "tensor_frac": setup_flop / (setup_device_ms * 1e-3) / 1e12 / tf32_peak,
+                          "note": "whole PreparePreconditioner (device time); tf32 peak = half the measured dense bf16 peak; the kernel is "
+                                  "bound by its serial per-panel chain (pivot inverse -> operand store -> MMA), not by either roof"}}
 
     # ---- PCG to 1e-5 with MAS through the device harness (BASELINE config 2: iteration count and wall time)
     pcg = None
@@ -439,12 +550,35 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline and not args.lean:
         threads = host_threads()
         n_cpu = 10
-        mean_rate, best_rate, cpu_setup_ms, kind = cpu_reference_apply(mesh, S.residual(nv), n_cpu, 1, threads)
+        mean_rate, best_rate, cpu_setup_ms, kind = cpu_reference_apply(mesh, r_np, n_cpu, 1, threads)
         cpu = {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
                "sample": f"whole {WORKLOADS[args.config]} mesh: 1 setup + 1 warm-up + {n_cpu} timed applies, all host threads",
                "best_ms": 1e3 / best_rate, "setup_ms": cpu_setup_ms}
+        # value parity at full size: the z of the timed GPU path against the reference's z on the same mesh and r, and both
+        # against FP64 arithmetic (the plain-C restatement built in double: the arbiter of SURVEY 8c)
+        z_ref = cpu_reference_apply.last_z
+        g.Preconditioning(z_h, r_h)
+        z_gpu = z_h.numpy()
+        rel = lambda a, b: float(np.linalg.norm((a - b)[:, :3].astype(np.float64)) / np.linalg.norm(b[:, :3].astype(np.float64)))
+        parity = {"rel_l2_gpu_vs_reference": rel(z_gpu, z_ref), "reference_kind": kind}
+        if not args.no_arbiter:
+            try:
+                from oracle import oracle_binding as ob
+                t0 = time.perf_counter()
+                o64 = ob.OraclePreconditioner("d")
+                o64.allocate(mesh)
+                o64.prepare()
+                z64 = o64.apply(r_np)
+                parity.update({"rel_l2_gpu_vs_f64": rel(z_gpu, z64), "rel_l2_reference_vs_f64": rel(z_ref, z64),
+                               "arbiter": "plain-C restatement in double precision (oracle/mas_oracle.c)",
+                               "arbiter_s": time.perf_counter() - t0})
+                parity["ok"] = bool(parity["rel_l2_gpu_vs_f64"] <= 8 * parity["rel_l2_reference_vs_f64"] + 1e-6)
+                parity["tolerance"] = "|z_gpu - z_f64| <= 8 |z_ref - z_f64| + 1e-6 |z_f64| (tensor-core setup; 2x with --invert-variant 1)"
+                del o64
+            except Exception as exc:                      # noqa: BLE001
+                parity["arbiter_error"] = repr(exc)
         if args.cpu_pcg:
-            cpu["pcg"] = cpu_reference_pcg(mesh, S.residual(nv), threads)
+            cpu["pcg"] = cpu_reference_pcg(mesh, r_np, threads)
 
     if world > 1:
         # per-rank share of the algorithmic bytes against one GPU's HBM peak (whole apply; no kernel-only timing here)
@@ -458,55 +592,53 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": int(rank_bytes), "traffic": None,
                 "per_rank_fine_kernel_ms": per_rank_fine_ms,
                 "aligned_cuts": g.aligned_cuts}
-    # ---- e2e with the other host staging (MAS_OPT_HOST_PULL: a kernel pulls the page-locked residual through its device
-    # mapping instead of the copy engine; bit-identical z).  Which one is faster depends on the host (the copy engine reads
-    # host memory at 15-55 GB/s depending on the box, profiles/r01_pcie_staging.json), so both are timed and the better one is
-    # reported, by name.  Runs last and guarded: a failure here leaves every number above untouched.
+    # ---- e2e with the other ways a host caller can hand over r and z.  Runs last and guarded: a failure here leaves every
+    # number above untouched.
+    #   host_pull          MAS_OPT_HOST_PULL: a kernel pulls the page-locked residual instead of the copy engine (bit-identical)
+    #   pageable           plain malloc'd buffers, what the C++ drop-in class sees from a std::vector caller
+    #   pageable_registered   the same with MAS_OPT_REGISTER_HOST: the library page-locks the caller's buffers on first sight
     e2e_note = "mas_apply(MAS_MEM_HOST): pinned host r -> H2D -> apply graph -> D2H z, synchronous"
-    e2e_modes = {"copy_engine": e2e_rate}
-    e2e_staging = "copy_engine"
+    e2e_modes = {"pinned_copy_engine": e2e_rate}
+    e2e_staging = "pinned_copy_engine"
     if world == 1 and not args.lean:
         try:
             z_ce = z_h.clone()
             g.set_option(7, 1)
-            for _ in range(3):
-                e2e_step()
-            torch.cuda.synchronize()
+            pull_rate = time_e2e(e2e_steps)
             identical = bool(torch.equal(z_h, z_ce))
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                e2e_step()
-            torch.cuda.synchronize()
-            pull_rate = e2e_steps / (time.perf_counter() - t0)
             g.set_option(7, 0)
             e2e_modes["host_pull"] = pull_rate
             e2e_modes["host_pull_bit_identical"] = identical
             if identical and pull_rate > e2e_rate:
                 e2e_rate, e2e_staging = pull_rate, "host_pull (MAS_OPT_HOST_PULL=1)"
+            r_pg, z_pg = r_np.copy(), np.zeros_like(r_np)
+            e2e_modes["pageable"] = time_e2e(e2e_steps, z_pg, r_pg)
+            g.set_option(9, 1)
+            e2e_modes["pageable_registered"] = time_e2e(e2e_steps, z_pg, r_pg)
+            e2e_modes["pageable_bit_identical"] = bool(np.array_equal(z_pg, z_ce.numpy()))
+            g.set_option(9, 0)
         except Exception as exc:                      # noqa: BLE001
-            e2e_modes["host_pull_error"] = repr(exc)
+            e2e_modes["error"] = repr(exc)
 
+    cfg["parallelism"] = ((f"morton-sharded x{world}, " + ("peer-memory exchange fused into the restriction kernel (NVLink)"
+                                                            if p2p else "NCCL all-reduce of coarse residuals"))
+                          if world > 1 else "single GPU")
     out = {
         "metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": "applies/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak" if (weak or world == 1 and args.scaling == "weak") else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "nv": nv, "levels": lv, "blocks": n_blocks,
-                   "units": (f"value = {units:g} x whole-mesh applies/s: one apply of the sharded {nv:,}-vertex mesh counts as "
-                             f"{units:g} applies of the 1M-vertex cloth (per-GPU work fixed)") if weak else "whole-mesh applies/s",
-                   "mesh_applies_per_s": 1e3 / ms_per_step,
-                   "l2": "inputs larger than L2: 630 MB of packed inverses streamed per step per GPU vs 126 MB L2",
-                   "timing": "CUDA events on the launching stream, max over ranks",
-                   "parallelism": (f"morton-sharded x{world}, " + ("peer-memory exchange fused into the restriction kernel (NVLink)"
-                                                                      if p2p else "NCCL all-reduce of coarse residuals"))
-                   if world > 1 else "single GPU"},
-        "setup_ms": setup_ms, "setup_device_ms": setup_device_ms, "invert_variant": args.invert_variant,
-        "e2e": {"value": units * e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": 16 * nv * world,
-                "d2h_bytes_per_step": 16 * nv * world, "steps": e2e_steps,
+        "config": cfg,
+        "mesh": {"nv": nv, "levels": lv, "blocks": n_blocks, "mesh_applies_per_s": 1e3 / ms_per_step,
+                 "exchange": "level-2 residuals over peer memory inside the apply graph" if p2p else ("NCCL all-reduce" if world > 1 else None)},
+        "setup_ms": setup_ms, "setup_device_ms": setup_device_ms, "setup_rebuild_hierarchy_ms": setup_full_ms,
+        "invert_variant": args.invert_variant,
+        "e2e": {"value": units * e2e_rate, "unit": "applies/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "staging": e2e_staging, "applies_per_s_by_staging": e2e_modes,
-                "note": "every rank copies the whole r in and its z out over its own PCIe link" if world > 1 else e2e_note},
+                "note": ("every rank moves only its own vertices' r and z over its own PCIe link (page-locked buffers)" if world > 1 else e2e_note)},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "pcg": pcg,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "pcg": pcg,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -528,6 +660,7 @@ def main():
     ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT: 0 = tcgen05 tensor cores (default), 1 = FP32 CUDA cores")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")
+    ap.add_argument("--no-arbiter", action="store_true", help="skip the FP64 arbiter of the in-run value parity (a few seconds per million vertices)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
