@@ -195,9 +195,10 @@ def test_register_host_option_keeps_results(gpu_cls, synth):
 def test_cached_hierarchy_gives_identical_setup(gpu_cls, synth):
     """MAS_OPT_CACHE_HIERARCHY (default on): collision-free prepares keep the clustering; a prepare with stencils rebuilds it."""
     m = synth.cloth(96, with_topology=True)
-    coll = synth.add_collisions(m, m.nv // 16, m.nv // 16, m.nv // 8)
+    coll = synth.add_collisions(synth.cloth(96, with_topology=True), m.nv // 16, m.nv // 16, m.nv // 8)   # (adds to its argument)
     stiff = synth.cloth(96, k=5000.0)
     r = synth.residual(m.nv)
+    assert m.ef_total == 0 and coll.ef_total > 0
 
     def run(cache):
         g = gpu_cls(0)
