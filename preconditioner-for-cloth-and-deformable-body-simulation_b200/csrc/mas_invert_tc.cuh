@@ -19,14 +19,16 @@
 // k/m = 10 .. 1e5 (tools/sweep_inversion_study.py replays this file's algorithm in numpy).  The 16x16 pivot
 // inverses, the products C P and all bookkeeping stay FP32 on the CUDA cores.
 //
-// Mapping: one CTA of 128 threads per system, persistent over systems, FOUR CTAs per SM (each owns 128 of the SM's 512 TMEM
-// columns; one CTA's serial chain — TMEM load, pivot inverse, C P, operand store, MMA — is hidden behind the other three).
+// Mapping: one CTA of 128 threads per system, persistent over systems, FIVE CTAs per SM: a CTA's serial chain — TMEM load,
+// pivot inverse, C P, operand store, MMA — is hidden behind the other four.  Tensor memory is allocated in powers of two, so
+// each CTA takes 64 + 32 of the SM's 512 columns (5 x 96 = 480) and every panel update is issued as two MMAs, N = 64 and
+// N = 32 (same tensor-pipe time as one N = 96); with one 128-column allocation only four CTAs fit (measured: 1.98 -> ms).
 // Thread r < 96 owns row r of T: TMEM lane r, read and written with the 32-lane x 32-bit shape, so the column panel C[r, :]
 // is one tcgen05.ld of 16 columns and (C P)[r, :] is thread-local.  Warp 3 has no rows: it inverts the pivot block in
 // registers (lanes = rows, shuffles broadcast the pivot row) while warps 0-2 zero row / column block K, and its lane 0 issues
 // the MMAs.  Operands are written to shared memory in the K-major no-swizzle core-matrix layout (mas_tcgen05.cuh).
 constexpr int kTcThreads = 128;
-constexpr int kTcCols = 128;            // TMEM columns per CTA (power of two >= 96); 4 CTAs x 128 = all 512 columns of an SM
+constexpr int kTcColsA = 64, kTcColsB = 32;   // TMEM columns per CTA: matrix columns 0..63 and 64..95 (two allocations)
 constexpr int kTcPs = 20;               // row stride of the 16x16 pivot scratch (16-byte aligned rows)
 
 struct TcOperands                       // 28 KB, K-major core-matrix layout, rows 96..127 of A stay zero
@@ -44,18 +46,27 @@ struct TcSmem
 	alignas(16) float piv[16 * kTcPs];          // pivot block T[K, K]
 	alignas(16) float P[16 * kTcPs];            // its inverse
 	float ownDiag[kBank][9];                    // assembly only, as in InvSmem
-	double folded[kBank][9];
 	int parent[kBank];
 	float fold[kBank][9];
 	alignas(8) uint64_t bar;                    // mbarrier: completion of a panel's MMAs
-	uint32_t tmemBase;
+	uint32_t tmemBase[2];                       // columns 0..63 and 64..95
+	int nextWork;                               // next system of this CTA (dynamic distribution)
+};
+// tensor-memory addresses of a CTA: matrix column c lives at colBase(c) (+ lane << 16)
+struct TcAddr
+{
+	uint32_t a, b;
+	__device__ __forceinline__ uint32_t col(int c) const { return c < kTcColsA ? a + (uint32_t)c : b + (uint32_t)(c - kTcColsA); }
 };
 
-// In-place un-pivoted Gauss-Jordan inverse of the 16x16 pivot block, one warp.  Lanes l and l + 16 hold the two halves
-// (8 columns each) of row l & 15; step p broadcasts row p and the pivot with shuffles, every row subtracts its multiple.
-//   d = 1 / M[p][p];   row p: M[p][j] *= d, M[p][p] = d;   row i != p: M[i][j] -= M[i][p] d M[p][j], M[i][p] = -M[i][p] d
-// The sixteen steps are one dependent chain (shuffle -> reciprocal -> multiply -> FMA), the serial part of every panel: no
-// divergent branches (the pivot row is the same FMA with base 0 and factor -d) and a two-instruction reciprocal.
+// In-place un-pivoted block Gauss-Jordan inverse of the 16x16 pivot block, one warp, 2x2 pivots.  Lanes l and l + 16 hold
+// the two halves (8 columns each) of row l & 15.  Step q takes the pivot pair P = {2q, 2q+1} with B = M[P, P]:
+//   rows of P:   M[P, j] <- B^-1 M[P, j] (j outside P),  M[P, P] <- B^-1
+//   other rows:  g = M[i, P] B^-1;  M[i, j] -= g M[P, j] (j outside P),  M[i, P] <- -g
+// i.e. two steps of the scalar elimination at once.  The eight steps are ONE dependent chain (shuffle -> determinant ->
+// reciprocal -> two FMAs deep), the serial part of every panel, so its length is what counts: the 2x2 pivots halve the number
+// of shuffle and reciprocal latencies against sixteen scalar steps (measured: 2.4 k -> cycles per panel), there is no
+// divergent branch (a pivot row is the same update with base 0 and g = -B^-1 row) and the reciprocal is MUFU + one Newton step.
 __device__ __forceinline__ float rcp_newton(const float x)
 {
 	float r;
@@ -72,20 +83,27 @@ __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, flo
 		m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
 	}
 #pragma unroll
-	for (int p = 0; p < 16; ++p)
+	for (int q = 0; q < 8; ++q)
 	{
-		const int ph = p >> 3, pc = p & 7;                                 // half and register holding column p
-		const float pivot = __shfl_sync(kAll, m[pc], p + 16 * ph);          // M[p][p]
-		const float mine = __shfl_sync(kAll, m[pc], row + 16 * ph);         // M[row][p]
-		float prow[8];
+		const int p = 2 * q, ph = p >> 3, pc = p & 7;                      // half and registers (pc, pc + 1) holding columns p, p + 1
+		const float b00 = __shfl_sync(kAll, m[pc], p + 16 * ph), b01 = __shfl_sync(kAll, m[pc + 1], p + 16 * ph);
+		const float b10 = __shfl_sync(kAll, m[pc], p + 1 + 16 * ph), b11 = __shfl_sync(kAll, m[pc + 1], p + 1 + 16 * ph);
+		const float f0 = __shfl_sync(kAll, m[pc], row + 16 * ph), f1 = __shfl_sync(kAll, m[pc + 1], row + 16 * ph);   // M[row][P]
+		float r0[8], r1[8];
 #pragma unroll
-		for (int c = 0; c < 8; ++c) prow[c] = __shfl_sync(kAll, m[c], p + 16 * half);   // M[p][my columns]
-		const float d = rcp_newton(pivot);
-		const bool isP = row == p;
-		const float g = isP ? -d : __fmul_rn(mine, d);
+		for (int c = 0; c < 8; ++c)
+		{
+			r0[c] = __shfl_sync(kAll, m[c], p + 16 * half);                // M[p][my columns]
+			r1[c] = __shfl_sync(kAll, m[c], p + 1 + 16 * half);            // M[p + 1][my columns]
+		}
+		const float rd = rcp_newton(__fmaf_rn(b00, b11, -__fmul_rn(b01, b10)));
+		const float i00 = __fmul_rn(b11, rd), i01 = -__fmul_rn(b01, rd), i10 = -__fmul_rn(b10, rd), i11 = __fmul_rn(b00, rd);
+		const bool isP0 = row == p, isP1 = row == p + 1, isP = isP0 || isP1;
+		const float g0 = isP0 ? -i00 : (isP1 ? -i10 : __fmaf_rn(f0, i00, __fmul_rn(f1, i10)));
+		const float g1 = isP0 ? -i01 : (isP1 ? -i11 : __fmaf_rn(f0, i01, __fmul_rn(f1, i11)));
 #pragma unroll
-		for (int c = 0; c < 8; ++c) m[c] = __fmaf_rn(-g, prow[c], isP ? 0.0f : m[c]);
-		if (half == ph) m[pc] = -g;                                         // d for the pivot row, -M[row][p] d elsewhere
+		for (int c = 0; c < 8; ++c) m[c] = __fmaf_rn(-g1, r1[c], __fmaf_rn(-g0, r0[c], isP ? 0.0f : m[c]));
+		if (half == ph) { m[pc] = -g0; m[pc + 1] = -g1; }
 	}
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0) = make_float4(m[0], m[1], m[2], m[3]);
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0 + 4) = make_float4(m[4], m[5], m[6], m[7]);
@@ -110,11 +128,11 @@ __device__ __forceinline__ void store_operand_row(float* __restrict__ hiBuf, flo
 // In: s.A holds the assembled 96x96 system (row stride kLdP), all threads past the barrier that completed it.
 // Out: s.packed holds the packed inverse (lane-slot layout, mas_internal.h), all threads past a barrier.
 // pos96[r * 96 + c], r >= c: packed position of symmetric element (r, c).  `parity`: phase of s.bar, carried across systems.
-__device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uint32_t& parity, const unsigned short* __restrict__ pos96,
+__device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint32_t& parity, const unsigned short* __restrict__ pos96,
 	int* __restrict__ errFlag, PhaseClock& pc)
 {
 	const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-	const uint32_t myRow = tc::tmem_at(tb, 32 * warp, 0);       // TMEM address of this thread's row (the hardware adds the lane)
+	const uint32_t myLane = (uint32_t)(32 * warp) << 16;        // lane field of this warp's TMEM quadrant (the hardware adds the lane)
 
 	// padding nodes: zero (0,0) entry of the diagonal block -> identity (cpp:1365-1368)
 	if (t < kBank && s.A[tile_at(3 * t, 3 * t)] == 0.0f)
@@ -133,7 +151,7 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 			float v[16];
 #pragma unroll
 			for (int j = 0; j < 16; ++j) v[j] = s.A[tile_at(t, c0 + j)];
-			tc::tmem_st16(myRow + c0, v);
+			tc::tmem_st16(tb.col(c0) + myLane, v);
 		}
 		tc::tmem_wait_st();
 	}
@@ -167,7 +185,7 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 		float c[16];
 		if (warp < 3)
 		{
-			tc::tmem_ld16(myRow + 16 * K, c);              // C[r, :], and for the rows of block K the pivot block itself
+			tc::tmem_ld16(tb.col(16 * K) + myLane, c);              // C[r, :], and for the rows of block K the pivot block itself
 			if ((t >> 4) == K)
 			{
 				float4* dst = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
@@ -183,11 +201,11 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 		{
 			// row and column block K of T are REPLACED by this panel: zero them, the GEMM then deposits the new values
 			const float zero[16] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-			tc::tmem_st16(myRow + 16 * K, zero);
+			tc::tmem_st16(tb.col(16 * K) + myLane, zero);
 			if (warp == (K >> 1))
 			{
-				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb, 16 * K, 0));
-				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb, 16 * K, 64));
+				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb.a, 16 * K, 0));      // columns 0..63
+				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb.b, 16 * K, 0));      // columns 64..95
 			}
 			// the B operand does not need P: Bop = C[r, :], and -I[x, :] for the rows of block K
 			if ((t >> 4) == K)
@@ -247,15 +265,21 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 		if (t == 96)
 		{
 			tc::fence_after_sync();
-			constexpr uint32_t id = tc::idesc_tf32(128, 96);
+			constexpr uint32_t idA = tc::idesc_tf32(128, kTcColsA), idB = tc::idesc_tf32(128, kTcColsB);
+			constexpr uint32_t rowsB = tc::operand_bytes(kTcColsA);       // B operand rows 64..95 feed matrix columns 64..95
 			const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
 #pragma unroll
 			for (int ks = 0; ks < 2; ++ks)
 			{
 				const uint32_t off = ks * 2 * tc::kLbo;
-				tc::mma_tf32(tb, tc::smem_desc(aL + off, tc::kLbo, tc::kSbo), tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), id, 1u);   // small terms first
-				tc::mma_tf32(tb, tc::smem_desc(aH + off, tc::kLbo, tc::kSbo), tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), id, 1u);
-				tc::mma_tf32(tb, tc::smem_desc(aH + off, tc::kLbo, tc::kSbo), tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), id, 1u);
+				const uint64_t dAl = tc::smem_desc(aL + off, tc::kLbo, tc::kSbo), dAh = tc::smem_desc(aH + off, tc::kLbo, tc::kSbo);
+				// small terms first: lo * hi, hi * lo, hi * hi; each as N = 64 (columns 0..63) and N = 32 (columns 64..95)
+				tc::mma_tf32(tb.a, dAl, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAl, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
+				tc::mma_tf32(tb.a, dAh, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAh, tc::smem_desc(bL + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
+				tc::mma_tf32(tb.a, dAh, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAh, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
 			}
 			tc::mma_commit(&s.bar);
 		}
@@ -274,7 +298,7 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 			float v[16];
 			const uint4 p0 = *reinterpret_cast<const uint4*>(pos96 + t * kDof + c0), p1 = *reinterpret_cast<const uint4*>(pos96 + t * kDof + c0 + 8);
 			const unsigned pw[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };      // sixteen 16-bit positions
-			tc::tmem_ld16(myRow + c0, v);
+			tc::tmem_ld16(tb.col(c0) + myLane, v);
 #pragma unroll
 			for (int j = 0; j < 16; ++j)
 				if (c0 + j <= t) s.packed[(pw[j >> 1] >> (16 * (j & 1))) & 0xffffu] = -v[j];
@@ -285,10 +309,15 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const uint32_t tb, uin
 	pc.mark(9);
 }
 
-// per-CTA set-up and tear-down of the tensor-memory allocation and the mbarrier
-__device__ __forceinline__ uint32_t tc_begin(TcSmem& s)
+// per-CTA set-up and tear-down of the tensor-memory allocations and the mbarrier
+__device__ __forceinline__ TcAddr tc_begin(TcSmem& s)
 {
-	if (threadIdx.x < 32) tc::tmem_alloc<kTcCols>(&s.tmemBase);
+	if (threadIdx.x < 32)
+	{
+		tc::tmem_alloc_only<kTcColsA>(&s.tmemBase[0]);
+		tc::tmem_alloc_only<kTcColsB>(&s.tmemBase[1]);
+		tc::tmem_relinquish();
+	}
 	if (threadIdx.x == 32)
 	{
 		tc::mbar_init(&s.bar, 1);
@@ -297,11 +326,28 @@ __device__ __forceinline__ uint32_t tc_begin(TcSmem& s)
 	tc::fence_before_sync();
 	__syncthreads();
 	tc::fence_after_sync();
-	return s.tmemBase;
+	TcAddr tb;
+	tb.a = s.tmemBase[0];
+	tb.b = s.tmemBase[1];
+	return tb;
 }
-__device__ __forceinline__ void tc_end(const uint32_t tb)
+__device__ __forceinline__ void tc_end(const TcAddr tb)
 {
 	tc::fence_before_sync();
 	__syncthreads();
-	if (threadIdx.x < 32) tc::tmem_dealloc<kTcCols>(tb);
+	if (threadIdx.x < 32)
+	{
+		tc::tmem_dealloc<kTcColsA>(tb.a);
+		tc::tmem_dealloc<kTcColsB>(tb.b);
+	}
+}
+
+// Dynamic distribution of the systems over the persistent CTAs: one counter per launch.  (A CTA that has to wait for tensor
+// memory — several contexts can share a GPU — then simply takes fewer systems.)  Returns the next index, the same in every
+// thread; contains a barrier.
+__device__ __forceinline__ int tc_next_work(TcSmem& s, int* __restrict__ counter)
+{
+	if (threadIdx.x == 0) s.nextWork = atomicAdd(counter, 1);
+	__syncthreads();
+	return s.nextWork;
 }

@@ -98,12 +98,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
 // address = (lane << 16) | column.  A warp reaches the 32 lanes of its own quadrant, lanes 32 * (warp % 4) ... + 31.
 __device__ __forceinline__ uint32_t tmem_at(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
 
-// one warp: allocate nCols (power of two >= 32) columns, address lands in *slot (shared memory); then let other CTAs allocate
+// one warp: allocate nCols (power of two >= 32) columns, address lands in *slot (shared memory); after the CTA's last
+// allocation tmem_relinquish() lets the other CTAs of the SM allocate without waiting for this one to exit
+template <int nCols>
+__device__ __forceinline__ void tmem_alloc_only(uint32_t* slot)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(slot)), "n"(nCols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
 template <int nCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot)
 {
-	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(slot)), "n"(nCols) : "memory");
-	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	tmem_alloc_only<nCols>(slot);
+	tmem_relinquish();
 }
 template <int nCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t base)
