@@ -13,6 +13,12 @@
 //                          Aop[x] = P[x, :],    Bop[x] = -I[x, :]        (x in K; row and column block K of T zeroed first)
 // which is what the tensor core is for: M = 128 (96 used) x N = 96 x K = 16 per panel, accumulated in place in TMEM.
 //
+// The product C P is a GEMM as well (96 x 16 x 16) and runs on the tensor core first: D[:, K] = C P^T lands in column block K
+// of T itself — exactly where (C P) has to end up — with the B operand buffer (the rows of C) as its A operand; the rows then
+// read their (C P)[i] back from tensor memory to form Aop, and the update GEMM leaves column block K alone (Bop[x] = 0 for
+// x in K; the 16 rows of block K store -P into it).  That took 340 of a row warp's 540 instructions per panel off the CUDA
+// cores (ncu: the kernel was at 43 % issue utilisation, FMA pipe 17 %, tensor pipe 13 %).
+//
 // Precision: kind::tf32 keeps 10 mantissa bits of each operand, which misses the parity bar by three orders of magnitude;
 // every operand is split into hi + lo TF32 halves and the three products lo*hi + hi*lo + hi*hi are accumulated in FP32
 // (3xTF32: six tcgen05.mma per panel), which is indistinguishable from FP32 arithmetic on the oracle's blocks at
@@ -44,10 +50,17 @@ struct TcSmem
 		float packed[kTri];                     // packed inverse (epilogue)
 	};
 	alignas(16) float piv[16 * kTcPs];          // pivot block T[K, K]
-	alignas(16) float P[16 * kTcPs];            // its inverse
-	float ownDiag[kBank][9];                    // assembly only, as in InvSmem
-	int parent[kBank];
-	float fold[kBank][9];
+	alignas(16) float P[16 * kTcPs];            // its inverse (FP32, row stride kTcPs)
+	union
+	{
+		struct                                  // assembly only, as in InvSmem
+		{
+			float ownDiag[kBank][9];
+			int parent[kBank];
+			float fold[kBank][9];
+		};
+		struct { alignas(128) float pHi[16 * 16], pLo[16 * 16]; };   // elimination: P as a tensor-core operand (hi / lo halves)
+	};
 	alignas(8) uint64_t bar;                    // mbarrier: completion of a panel's MMAs
 	uint32_t tmemBase[2];                       // columns 0..63 and 64..95
 	int nextWork;                               // next system of this CTA (dynamic distribution)
@@ -131,7 +144,9 @@ __device__ __forceinline__ void store_operand_row(float* __restrict__ hiBuf, flo
 __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint32_t& parity, const unsigned short* __restrict__ pos96,
 	int* __restrict__ errFlag, PhaseClock& pc)
 {
-	const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+	// the warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role branches below uniform
+	// (from threadIdx alone it cannot, and wraps every shuffle inside `if (warp == 3)` in a convergence sequence)
+	const int t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;
 	const uint32_t myLane = (uint32_t)(32 * warp) << 16;        // lane field of this warp's TMEM quadrant (the hardware adds the lane)
 
 	// padding nodes: zero (0,0) entry of the diagonal block -> identity (cpp:1365-1368)
@@ -182,92 +197,108 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 			tc::fence_after_sync();
 		}
 		pc.mark(4);
-		float c[16];
+		const uint32_t colK = tb.col(16 * K);              // TMEM address of column block K (lane 0)
+		const bool inK = (t >> 4) == K;                    // this thread's row belongs to block K
 		if (warp < 3)
 		{
-			tc::tmem_ld16(tb.col(16 * K) + myLane, c);              // C[r, :], and for the rows of block K the pivot block itself
-			if ((t >> 4) == K)
+			float c[16];
+			tc::tmem_ld16(colK + myLane, c);               // C[r, :], and for the rows of block K the pivot block itself
+			if (inK)
 			{
 				float4* dst = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
 #pragma unroll
 				for (int q = 0; q < 4; ++q) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+#pragma unroll
+				for (int k = 0; k < 16; ++k) c[k] = 0.0f;  // Bop[x] = 0 for the rows of block K
+			}
+			// Bop = C[r, :]: B operand of the update GEMM and A operand of the product C P
+			store_operand_row(s.op.bHi, s.op.bLo, t, c);
+			// row block K of T is REPLACED by this panel: zero it, the update GEMM then deposits P C^T there
+			if (warp == (K >> 1))
+			{
+				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb.a, 16 * K, 0));      // columns 0..63
+				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb.b, 16 * K, 0));      // columns 64..95
+				tc::tmem_wait_st();
 			}
 		}
 		__syncthreads();
 		pc.mark(5);
 		if (warp == 3)
-			invert16_warp(s.piv, s.P, lane);
-		else
 		{
-			// row and column block K of T are REPLACED by this panel: zero them, the GEMM then deposits the new values
-			const float zero[16] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-			tc::tmem_st16(tb.col(16 * K) + myLane, zero);
-			if (warp == (K >> 1))
-			{
-				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb.a, 16 * K, 0));      // columns 0..63
-				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb.b, 16 * K, 0));      // columns 64..95
-			}
-			// the B operand does not need P: Bop = C[r, :], and -I[x, :] for the rows of block K
-			if ((t >> 4) == K)
-			{
-				float e[16];
+			invert16_warp(s.piv, s.P, lane);
+			// P again as a tensor-core operand: row n = lane & 15, k = 8 (lane >> 4) .. + 7 (P is symmetric: B[n][k] = P[n][k])
+			const int row = lane & 15, c0 = 8 * (lane >> 4);
+			const float4 v0 = *reinterpret_cast<const float4*>(s.P + row * kTcPs + c0), v1 = *reinterpret_cast<const float4*>(s.P + row * kTcPs + c0 + 4);
+			const float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+			float hi[8], lo[8];
 #pragma unroll
-				for (int k = 0; k < 16; ++k) e[k] = (k == (t & 15)) ? -1.0f : 0.0f;
-				store_operand_row(s.op.bHi, s.op.bLo, t, e);
-			}
-			else
-				store_operand_row(s.op.bHi, s.op.bLo, t, c);
-			tc::tmem_wait_st();
+			for (int k = 0; k < 8; ++k) tc::split_tf32(v[k], hi[k], lo[k]);
+			unsigned char* h = reinterpret_cast<unsigned char*>(s.pHi) + tc::operand_offset(row, c0);
+			unsigned char* l = reinterpret_cast<unsigned char*>(s.pLo) + tc::operand_offset(row, c0);
+			*reinterpret_cast<float4*>(h) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+			*reinterpret_cast<float4*>(h + tc::kLbo) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+			*reinterpret_cast<float4*>(l) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+			*reinterpret_cast<float4*>(l + tc::kLbo) = make_float4(lo[4], lo[5], lo[6], lo[7]);
 		}
+		tc::fence_async_smem();
+		tc::fence_before_sync();
 		__syncthreads();
 		pc.mark(6);
+		const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
+		if (t == 96)
+		{
+			// T[:, K] = C P^T (3xTF32, small terms first; the first MMA overwrites the column block)
+			tc::fence_after_sync();
+			constexpr uint32_t idP = tc::idesc_tf32(128, 16);
+			const uint32_t pH = tc::smem_addr(s.pHi), pL = tc::smem_addr(s.pLo);
+#pragma unroll
+			for (int ks = 0; ks < 2; ++ks)
+			{
+				const uint32_t off = ks * 2 * tc::kLbo;
+				tc::mma_tf32(colK, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, ks);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pL + off, tc::kLbo, tc::kSbo), idP, 1u);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, 1u);
+			}
+			tc::mma_commit(&s.bar);
+		}
+		if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+		parity ^= 1u;
+		tc::fence_after_sync();
+		pc.mark(7);
 		if (warp < 3)
 		{
 			float a[16];
-			if ((t >> 4) == K)
+			tc::tmem_ld16(colK + myLane, a);               // (C P)[r, :]; zero for the rows of block K
+			if (warp == (K >> 1))
 			{
-				// rows of block K: Aop = P[x, :]
-				const float4* src = reinterpret_cast<const float4*>(s.P + (t & 15) * kTcPs);
-#pragma unroll
-				for (int q = 0; q < 4; ++q)
+				// the rows of block K store -P into the pivot block (their 16 lanes cannot be written alone with this shape:
+				// the other 16 rows of the warp write back what they have just read)
+				if (inK)
 				{
-					const float4 v = src[q];
-					a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-				}
-			}
-			else
-			{
-				// Aop = -(C P)[r, :]
-#pragma unroll
-				for (int k = 0; k < 16; ++k) a[k] = 0.0f;
-#pragma unroll
-				for (int j = 0; j < 16; ++j)
-				{
-					const float4* prow = reinterpret_cast<const float4*>(s.P + j * kTcPs);
-					const float cj = -c[j];
+					const float4* src = reinterpret_cast<const float4*>(s.P + (t & 15) * kTcPs);
 #pragma unroll
 					for (int q = 0; q < 4; ++q)
 					{
-						const float4 v = prow[q];
-						a[4 * q] = __fmaf_rn(cj, v.x, a[4 * q]);
-						a[4 * q + 1] = __fmaf_rn(cj, v.y, a[4 * q + 1]);
-						a[4 * q + 2] = __fmaf_rn(cj, v.z, a[4 * q + 2]);
-						a[4 * q + 3] = __fmaf_rn(cj, v.w, a[4 * q + 3]);
+						const float4 v = src[q];
+						a[4 * q] = -v.x; a[4 * q + 1] = -v.y; a[4 * q + 2] = -v.z; a[4 * q + 3] = -v.w;
 					}
 				}
+				tc::tmem_st16(colK + myLane, a);
+				tc::tmem_wait_st();
 			}
+			// Aop = -(C P)[r, :] for the rows outside block K, P[x, :] for the rows of block K: the negative of `a` either way
+#pragma unroll
+			for (int k = 0; k < 16; ++k) a[k] = -a[k];
 			store_operand_row(s.op.aHi, s.op.aLo, t, a);
 		}
 		tc::fence_async_smem();
 		tc::fence_before_sync();
 		__syncthreads();
-		pc.mark(7);
 		if (t == 96)
 		{
 			tc::fence_after_sync();
 			constexpr uint32_t idA = tc::idesc_tf32(128, kTcColsA), idB = tc::idesc_tf32(128, kTcColsB);
 			constexpr uint32_t rowsB = tc::operand_bytes(kTcColsA);       // B operand rows 64..95 feed matrix columns 64..95
-			const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
 #pragma unroll
 			for (int ks = 0; ks < 2; ++ks)
 			{
