@@ -86,7 +86,8 @@ __device__ __forceinline__ float rcp_newton(const float x)
 	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
 	return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
 }
-__device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, float* __restrict__ P, const int lane)
+__device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, float* __restrict__ P, float* __restrict__ pHi,
+	float* __restrict__ pLo, const int lane)
 {
 	constexpr unsigned kAll = 0xffffffffu;
 	const int row = lane & 15, half = lane >> 4, c0 = 8 * half;
@@ -120,6 +121,16 @@ __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, flo
 	}
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0) = make_float4(m[0], m[1], m[2], m[3]);
 	*reinterpret_cast<float4*>(P + row * kTcPs + c0 + 4) = make_float4(m[4], m[5], m[6], m[7]);
+	// P again as a tensor-core operand (B of the product C P^T: row n = this lane's row, k = c0 .. c0 + 7; P is symmetric)
+	float hi[8], lo[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) tc::split_tf32(m[k], hi[k], lo[k]);
+	unsigned char* h = reinterpret_cast<unsigned char*>(pHi) + tc::operand_offset(row, c0);
+	unsigned char* l = reinterpret_cast<unsigned char*>(pLo) + tc::operand_offset(row, c0);
+	*reinterpret_cast<float4*>(h) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+	*reinterpret_cast<float4*>(h + tc::kLbo) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+	*reinterpret_cast<float4*>(l) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+	*reinterpret_cast<float4*>(l + tc::kLbo) = make_float4(lo[4], lo[5], lo[6], lo[7]);
 }
 
 // one operand row (16 k) of thread / row `r`: hi and lo halves, four 16-byte stores each
@@ -199,9 +210,9 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 		pc.mark(4);
 		const uint32_t colK = tb.col(16 * K);              // TMEM address of column block K (lane 0)
 		const bool inK = (t >> 4) == K;                    // this thread's row belongs to block K
+		float c[16];
 		if (warp < 3)
 		{
-			float c[16];
 			tc::tmem_ld16(colK + myLane, c);               // C[r, :], and for the rows of block K the pivot block itself
 			if (inK)
 			{
@@ -211,7 +222,12 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 #pragma unroll
 				for (int k = 0; k < 16; ++k) c[k] = 0.0f;  // Bop[x] = 0 for the rows of block K
 			}
-			// Bop = C[r, :]: B operand of the update GEMM and A operand of the product C P
+		}
+		__syncthreads();
+		pc.mark(5);
+		if (warp < 3)
+		{
+			// (beside warp 3 inverting the pivot block)  Bop = C[r, :]: B operand of the update GEMM and A operand of C P
 			store_operand_row(s.op.bHi, s.op.bLo, t, c);
 			// row block K of T is REPLACED by this panel: zero it, the update GEMM then deposits P C^T there
 			if (warp == (K >> 1))
@@ -221,24 +237,9 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 				tc::tmem_wait_st();
 			}
 		}
-		__syncthreads();
-		pc.mark(5);
 		if (warp == 3)
 		{
-			invert16_warp(s.piv, s.P, lane);
-			// P again as a tensor-core operand: row n = lane & 15, k = 8 (lane >> 4) .. + 7 (P is symmetric: B[n][k] = P[n][k])
-			const int row = lane & 15, c0 = 8 * (lane >> 4);
-			const float4 v0 = *reinterpret_cast<const float4*>(s.P + row * kTcPs + c0), v1 = *reinterpret_cast<const float4*>(s.P + row * kTcPs + c0 + 4);
-			const float v[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
-			float hi[8], lo[8];
-#pragma unroll
-			for (int k = 0; k < 8; ++k) tc::split_tf32(v[k], hi[k], lo[k]);
-			unsigned char* h = reinterpret_cast<unsigned char*>(s.pHi) + tc::operand_offset(row, c0);
-			unsigned char* l = reinterpret_cast<unsigned char*>(s.pLo) + tc::operand_offset(row, c0);
-			*reinterpret_cast<float4*>(h) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-			*reinterpret_cast<float4*>(h + tc::kLbo) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-			*reinterpret_cast<float4*>(l) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-			*reinterpret_cast<float4*>(l + tc::kLbo) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+			invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
 		}
 		tc::fence_async_smem();
 		tc::fence_before_sync();
