@@ -224,7 +224,7 @@ def run_reference(args):
         return
     pkg = importlib.import_module(PKG_NAME)
     cfg, units, _ = workload_and_config(args, max(world, args.gpus))
-    mesh = pkg.synth.config(args.config)      # the CPU arm times one unit (the BASELINE mesh) on all host threads
+    mesh = pkg.synth.config(args.config, proximity=getattr(args, "proximity", False))      # one unit on all host threads
     r = pkg.synth.residual(mesh.nv)
     threads = host_threads()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -273,6 +273,9 @@ def run_ours(args):
         mesh = S.cloth_rect_device(1024 * a, 1024 * b, torch.device(dev))
     elif args.config == 4:
         mesh = S.cloth_rect_device(2048, 2048, torch.device(dev))      # strong scaling: the 4.2M-vertex cloth split N ways
+    elif args.config == 1 and args.proximity:
+        mesh = S.config(1, proximity=True)
+        cfg["workload"] = f"cloth 512x512 (262,144 verts) folded in half + proximity EF/EE/VF stencils ({mesh.ef_total}/{mesh.ee_total}/{mesh.vf_total})"
     else:
         mesh = S.config(args.config)
     nv = mesh.nv
@@ -416,6 +419,50 @@ def run_ours(args):
             one.close()
             del z1
         del merged, covered
+
+    # ---- BASELINE config 4 beside the headline (its strong-scaling curve rides on the driver's 1/2/4/8-GPU runs of the default
+    # command): the 2048^2 cloth (4,194,304 vertices, five levels) split over the same N ranks, HBM-resident applies/s
+    strong4 = None
+    if args.config == 2 and not args.lean and not args.no_strong:
+        try:
+            m4 = S.cloth_rect_device(2048, 2048, torch.device(dev))
+            e4 = pkg.SeSchwarzPreconditioner(device=local, rank=rank, world=world, stream=stream)
+            e4.m_positions, e4.m_neighbours = m4.positions, (m4.nbr_starts, m4.nbr_idx)
+            e4.AllocatePrecoditioner(m4.nv, 0, 0)
+            p2p4 = False
+            if world > 1:
+                p2p4 = pkg.partition.ShardedSchwarzPreconditioner(e4).attach_peers()
+                e4.PreparePreconditioner(m4.diag, m4.offdiag, m4.nbr_starts, phase="begin")
+                dist.all_reduce(e4.exchange_tensor(0))
+                e4.prepare_end()
+            else:
+                e4.PreparePreconditioner(m4.diag, m4.offdiag, m4.nbr_starts)
+            if world == 1 or p2p4:
+                r4 = t(S.residual(m4.nv))
+                z4 = torch.zeros_like(r4)
+                for _ in range(5):
+                    e4.Preconditioning(z4, r4)
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n4 = max(20, min(args.steps, 100))
+                a0.record()
+                for _ in range(n4):
+                    e4.Preconditioning(z4, r4)
+                a1.record()
+                barrier()
+                t4 = torch.tensor([a0.elapsed_time(a1) / n4], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+                    e4.synchronize()
+                strong4 = {"workload": WORKLOADS[4] + (f", Morton-sharded over {world} GPUs" if world > 1 else ""), "n_gpus": world,
+                           "applies_per_s": 1e3 / float(t4.item()), "ms_per_apply": float(t4.item()), "steps": n4,
+                           "scaling": "strong", "levels": e4.level_size().tolist()}
+                del r4, z4
+            e4.close()
+            del m4, e4
+            torch.cuda.empty_cache()
+        except Exception as exc:                      # noqa: BLE001
+            strong4 = {"error": repr(exc)}
 
     # ---- e2e: public host-pointer API, pinned host buffers, H2D + apply + D2H inside the timed region
     r_np = S.residual(nv)
@@ -639,6 +686,7 @@ def run_ours(args):
                 "note": ("every rank moves only its own vertices' r and z over its own PCIe link (page-locked buffers)" if world > 1 else e2e_note)},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "pcg": pcg,
+        "strong_scaling_config4": strong4,
     }
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -660,6 +708,8 @@ def main():
     ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT: 0 = tcgen05 tensor cores (default), 1 = FP32 CUDA cores")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")
+    ap.add_argument("--proximity", action="store_true", help="config 1: folded sheet with the stencils of the proximity producer (collide.py)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the BASELINE config 4 (2048^2) strong-scaling measurement beside the headline")
     ap.add_argument("--no-arbiter", action="store_true", help="skip the FP64 arbiter of the in-run value parity (a few seconds per million vertices)")
     args = ap.parse_args()
     if args.impl == "reference":

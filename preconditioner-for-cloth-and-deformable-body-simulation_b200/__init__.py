@@ -5,6 +5,7 @@ V-Sekai/preconditioner-for-cloth-and-deformable-body-simulation (class SE::SeSch
                   device code (mas_invert.cuh) is also compiled for the host by tests/emu (thread-block emulation)
   schwarz.py      host-side mirror of the reference class over that C ABI (ctypes)
   synth.py        deterministic synthetic inputs for the BASELINE.json configs
+  collide.py      proximity-based EF / EE / VF stencil producer (caller-side workload generation, torch tensor ops)
   pcg.py          caller-side PCG loop (the reference ships none) over mas_pcg_solve, used for iteration-count parity
   partition.py    multi-GPU host side: Morton-contiguous shards, begin -> exchange -> end driver
 
@@ -14,4 +15,5 @@ The directory name contains hyphens; import it with
 from .schwarz import SeSchwarzPreconditioner, MasError, load_library, LIB_PATH, EXPORTS  # noqa: F401
 from . import synth  # noqa: F401
 from . import partition  # noqa: F401
+from . import collide  # noqa: F401
 from .pcg import pcg_solve, PcgResult  # noqa: F401

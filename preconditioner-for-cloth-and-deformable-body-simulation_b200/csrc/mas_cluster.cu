@@ -19,6 +19,9 @@
 //  * stencils are compacted in input order (the reference's order is
 //    thread-timing dependent, cpp:407).
 #include "mas_internal.h"
+#ifndef MAS_CPU_EMULATION
+#include <cub/device/device_scan.cuh>
+#endif
 
 #include <utility>
 
@@ -332,9 +335,27 @@ __global__ void find_cuts_kernel(const int* __restrict__ bankPrefix, int nBanks,
 }  // namespace
 
 #ifndef MAS_CPU_EMULATION   // host side: launches (tests/emu/cluster_emu.cpp, test infrastructure, has its own launcher)
+// Exclusive scan + total.  Up to 64 k elements (meshes up to 2M vertices: one element per 32-node bank) the single CTA above
+// is the fastest thing there is (one launch, no temporary storage); beyond that it serialises (151 ms of setup at 33.5M
+// vertices went into it) and CUB's decoupled look-back scan takes over, followed by a one-thread kernel for the total.
+__global__ void scan_total_kernel(const int* __restrict__ in, const int* __restrict__ out, int count, int* __restrict__ totalOut)
+{
+	*totalOut = count > 0 ? out[count - 1] + in[count - 1] : 0;
+}
+
 int launch_exclusive_scan(Context* c, const int* in, int count, int* out, int* totalOut)
 {
-	exclusive_scan_kernel<<<1, kScanThreads, 0, c->stream>>>(in, count, out, totalOut);
+	if (count <= 65536)
+	{
+		exclusive_scan_kernel<<<1, kScanThreads, 0, c->stream>>>(in, count, out, totalOut);
+		MAS_CUDA(c, cudaGetLastError());
+		return MAS_OK;
+	}
+	size_t bytes = 0;
+	MAS_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, c->stream));
+	if (int rc = reserve(c, c->cubTemp, bytes)) return rc;
+	MAS_CUDA(c, cub::DeviceScan::ExclusiveSum(c->cubTemp.p, bytes, in, out, count, c->stream));
+	scan_total_kernel<<<1, 1, 0, c->stream>>>(in, out, count, totalOut);
 	MAS_CUDA(c, cudaGetLastError());
 	return MAS_OK;
 }
@@ -353,7 +374,7 @@ int build_stencils(Context* c, const void* ef, const void* ee, const void* vf, u
 	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
 	stencil_flag_kernel<<<cdiv(n, threads), threads, 0, s>>>((const unsigned char*)ef, (const unsigned char*)ee,
 		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->optStencilFix, c->stencilFlag.p);
-	exclusive_scan_kernel<<<1, kScanThreads, 0, s>>>(c->stencilFlag.p, n, c->stencilSlot.p, c->scanTotal.p);
+	if (int rc = launch_exclusive_scan(c, c->stencilFlag.p, n, c->stencilSlot.p, c->scanTotal.p)) return rc;
 	c->prepareLaunches += 2;
 	int count = 0;
 	MAS_CUDA(c, cudaMemcpyAsync(&count, c->scanTotal.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -379,7 +400,7 @@ static int number_level(Context* c, unsigned* mask, int count, int addSelf, int 
 	if (int rc = reserve(c, c->bankPrefix, (size_t)nBanks)) return rc;
 	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
 	close_components_kernel<<<cdiv((long long)nBanks * 32, threads), threads, 0, s>>>(mask, count, addSelf, c->bankCount.p);
-	exclusive_scan_kernel<<<1, kScanThreads, 0, s>>>(c->bankCount.p, nBanks, c->bankPrefix.p, c->scanTotal.p);
+	if (int rc = launch_exclusive_scan(c, c->bankCount.p, nBanks, c->bankPrefix.p, c->scanTotal.p)) return rc;
 	// node ids of the next level start right after this level's padded range
 	const int nextBegin = begin + pad32(count);
 	// goingNext must hold [0, nextBegin)

@@ -418,6 +418,32 @@ def rippled_cloth(n: int = 64, amplitude: float = 1e-4, k: float = 1000.0) -> Me
     return from_edges(pos, a, b, k=k, name=f"rippled{n}")
 
 
+def folded_cloth(nx: int = 64, ny: int = 64, gap: float = 0.004, wobble: float = 0.006, k: float = 1000.0, m: float = 1.0,
+                 spacing: float = 0.01) -> Mesh:
+    """An nx x ny sheet folded in half along x: the second half lies back over the first at height gap + wobble sin(...),
+    shifted by a fraction of a cell so that no two vertices share their (x, y).  Where the wobble exceeds the gap the layers
+    interpenetrate (edges pierce faces: EF stencils); elsewhere they are within a fraction of an edge length of each other
+    (VF / EE stencils).  Geometry for collide.proximity_stencils; springs and topology as in cloth_rect."""
+    mesh = cloth_rect(nx, ny, k, m, with_topology=True, spacing=spacing)
+    s = np.float32(spacing)
+    i = (np.arange(mesh.nv) % nx).astype(np.float32)
+    j = (np.arange(mesh.nv) // nx).astype(np.float32)
+    half = np.float32(nx // 2)
+    upper = i > half
+    pos = mesh.positions.copy()
+    pos[upper, 0] = s * (2 * half - i[upper]) + np.float32(0.37) * s
+    pos[upper, 1] = s * j[upper] + np.float32(0.21) * s
+    pos[upper, 2] = np.float32(gap) + np.float32(wobble) * np.sin(np.float32(0.35) * i[upper]) * np.cos(np.float32(0.27) * j[upper])
+    # the fold itself: a short ramp so that the crease column does not stretch to the full gap in one edge
+    crease = i == half + 1
+    pos[crease, 2] *= np.float32(0.5)
+    mesh.positions = pos.astype(np.float32)
+    src = np.repeat(np.arange(mesh.nv), np.diff(mesh.nbr_starts))
+    mesh.diag, mesh.offdiag = _spring_hessian(mesh.positions, mesh.nbr_starts, mesh.nbr_idx, src, k, m, 0.0)
+    mesh.name = f"folded{nx}x{ny}"
+    return mesh
+
+
 def dust(n: int = 6000, seed: int = 2, m: float = 1.0) -> Mesh:
     """n free particles, no edges at all: nothing ever aggregates, so EVERY level keeps n one-vertex clusters (three
     times the reference's whole fixed allocation at n = 6000, Q6) and every domain matrix is m I.  Known answer without
@@ -446,10 +472,14 @@ def fnv1a_i32(values: np.ndarray) -> int:
     return h
 
 
-def config(index: int) -> Mesh:
-    """BASELINE.json configs[index]."""
+def config(index: int, proximity: bool = False) -> Mesh:
+    """BASELINE.json configs[index].  proximity (config 1 only): the 512x512 sheet folded in half, with the EF / EE / VF
+    stencils collide.proximity_stencils finds between the two layers instead of the random synthetic ones."""
     if index == 0:
         return cloth(64)
+    if index == 1 and proximity:
+        from .collide import proximity_stencils
+        return proximity_stencils(folded_cloth(512, 512), radius=0.006)
     if index == 1:
         mesh = cloth(512, with_topology=True)
         return add_collisions(mesh, mesh.nv // 16, mesh.nv // 16, mesh.nv // 8)

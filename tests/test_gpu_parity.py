@@ -35,12 +35,20 @@ def _cases(synth):
         "chain32_exactly_one_bank": lambda: synth.chain(32),
         "chain33_one_over": lambda: synth.chain(33),
         "chain100_fragmented_banks": lambda: synth.chain(100),    # bent line: many components per Morton bank
+        # folded sheet with the EF / EE / VF stencils of the proximity producer (collide.py, run on the GPU here)
+        "folded64_proximity": lambda: _collide().proximity_stencils(synth.folded_cloth(64, 64), radius=0.006),
     }
+
+
+def _collide():
+    import importlib
+    return importlib.import_module("preconditioner-for-cloth-and-deformable-body-simulation_b200.collide")
 
 
 CASE_NAMES = ["cloth64", "cloth50_ragged", "cloth7_tiny", "cloth5_single_bank", "cloth64_skew", "cloth96_collisions",
               "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff", "cloth_rect96x40", "cloth20_isolated_vertices",
-              "chain1_single_vertex", "chain32_exactly_one_bank", "chain33_one_over", "chain100_fragmented_banks"]
+              "chain1_single_vertex", "chain32_exactly_one_bank", "chain33_one_over", "chain100_fragmented_banks",
+              "folded64_proximity"]
 
 
 @pytest.fixture(scope="module")
