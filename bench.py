@@ -169,7 +169,7 @@ def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
     # beyond 33,792 level-1 nodes (nv > 1,081,344) the stock reference truncates a scan (Q5, cpp:989-994) and then overruns
     # its own buffers (observed: segfault at 2048^2): such meshes are timed on the build with that four-line cull removed
     big = mesh.nv > 33792 * 32
-    if rb.available(q5fix=big):
+    if rb.available(q5fix=big) and not os.environ.get("MAS_BENCH_FORCE_PORT"):
         p = rb.RefPreconditioner(threads=threads, q5fix=big)
         kind = "reference"
     else:
@@ -195,6 +195,56 @@ def cpu_reference_apply(mesh, r, steps: int, warmup: int, threads: int):
     mean = (time.perf_counter() - t_all) / steps
     cpu_reference_apply.last_z = z          # the reference's z on this (mesh, r): value parity is checked against it
     return 1.0 / mean, 1.0 / best, setup_ms, kind
+
+
+def _mesh_to_npz(mesh, r, path):
+    import numpy as np
+    np.savez(path, name=mesh.name, nv=mesh.nv, positions=mesh.positions, nbr_starts=mesh.nbr_starts, nbr_idx=mesh.nbr_idx, diag=mesh.diag,
+             offdiag=mesh.offdiag, edges=mesh.edges, faces=mesh.faces, ef=mesh.ef, ee=mesh.ee, vf=mesh.vf,
+             totals=np.array([mesh.ef_total, mesh.ee_total, mesh.vf_total]), r=r)
+
+
+def _mesh_from_npz(path):
+    import numpy as np
+    pkg = importlib.import_module(PKG_NAME)
+    d = np.load(path)
+    m = pkg.synth.Mesh(str(d["name"]), int(d["nv"]), d["positions"], d["nbr_starts"], d["nbr_idx"], d["diag"], d["offdiag"], d["edges"], d["faces"],
+                       d["ef"], d["ee"], d["vf"], int(d["totals"][0]), int(d["totals"][1]), int(d["totals"][2]))
+    return m, d["r"]
+
+
+def cpu_leg_child(path, steps, warmup, threads, force_port):
+    """Internal (`bench.py --cpu-leg-child`): the CPU reference leg in a process of its own, so that a crash of the reference's
+    code (it overruns its fixed allocations on some inputs) cannot take the bench line down."""
+    import numpy as np
+    mesh, r = _mesh_from_npz(path)
+    if force_port:
+        os.environ["MAS_BENCH_FORCE_PORT"] = "1"
+    mean_rate, best_rate, setup_ms, kind = cpu_reference_apply(mesh, r, steps, warmup, threads)
+    np.save(path + ".z.npy", cpu_reference_apply.last_z)
+    print(json.dumps({"mean_rate": mean_rate, "best_rate": best_rate, "setup_ms": setup_ms, "kind": kind}), flush=True)
+
+
+def cpu_leg_isolated(mesh, r, steps, warmup, threads):
+    """Runs the CPU reference leg in a child process.  Returns (mean_rate, best_rate, setup_ms, kind, z_ref, note)."""
+    import tempfile
+    import numpy as np
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "mesh.npz")
+        _mesh_to_npz(mesh, r, path)
+        note = None
+        for force_port in (False, True):
+            cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg-child", path, "--steps", str(steps), "--warmup", str(warmup)]
+            if force_port:
+                cmd.append("--cpu-leg-port")
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=1800, env=dict(os.environ, MAS_BENCH_THREADS=str(threads)))
+            if p.returncode == 0 and p.stdout.strip():
+                res = json.loads(p.stdout.strip().splitlines()[-1])
+                z = np.load(path + ".z.npy")
+                return res["mean_rate"], res["best_rate"], res["setup_ms"], res["kind"], z, note
+            note = (f"the reference's own code crashed on this input (exit code {p.returncode}: it overruns its fixed allocations, SURVEY Q6); "
+                    "timed the plain-C port of the same algorithm instead")
+        raise RuntimeError("CPU reference leg failed twice: " + (p.stderr or "")[-300:])
 
 
 def cpu_reference_pcg(mesh, b, threads: int):
@@ -229,7 +279,9 @@ def run_reference(args):
     threads = host_threads()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     t0 = time.perf_counter()
-    mean_rate, best_rate, setup_ms, kind = cpu_reference_apply(mesh, r, steps, warmup, threads)
+    mean_rate, best_rate, setup_ms, kind, _, note = cpu_leg_isolated(mesh, r, steps, warmup, threads)
+    if kind != "reference":
+        threads = 1
     out = {
         "impl": "reference", "metric": METRIC, "value": mean_rate, "unit": "applies/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / mean_rate, "higher_is_better": True,
@@ -242,6 +294,8 @@ def run_reference(args):
         "e2e": {"value": mean_rate, "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
+    if note:
+        out["cpu_baseline"]["note"] = note
     print(json.dumps(out), flush=True)
 
 
@@ -597,13 +651,15 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline and not args.lean:
         threads = host_threads()
         n_cpu = 10
-        mean_rate, best_rate, cpu_setup_ms, kind = cpu_reference_apply(mesh, r_np, n_cpu, 1, threads)
-        cpu = {"value": mean_rate, "unit": "applies/s", "cores": threads, "kind": kind,
-               "sample": f"whole {WORKLOADS[args.config]} mesh: 1 setup + 1 warm-up + {n_cpu} timed applies, all host threads",
+        mean_rate, best_rate, cpu_setup_ms, kind, z_ref, cpu_note = cpu_leg_isolated(mesh, r_np, n_cpu, 1, threads)
+        cpu = {"value": mean_rate, "unit": "applies/s", "cores": threads if kind == "reference" else 1, "kind": kind,
+               "sample": f"whole {cfg['workload']} mesh: 1 setup + 1 warm-up + {n_cpu} timed applies, " +
+                         ("all host threads" if kind == "reference" else "one thread (scalar port)") + ", in a child process",
                "best_ms": 1e3 / best_rate, "setup_ms": cpu_setup_ms}
+        if cpu_note:
+            cpu["note"] = cpu_note
         # value parity at full size: the z of the timed GPU path against the reference's z on the same mesh and r, and both
         # against FP64 arithmetic (the plain-C restatement built in double: the arbiter of SURVEY 8c)
-        z_ref = cpu_reference_apply.last_z
         g.Preconditioning(z_h, r_h)
         z_gpu = z_h.numpy()
         rel = lambda a, b: float(np.linalg.norm((a - b)[:, :3].astype(np.float64)) / np.linalg.norm(b[:, :3].astype(np.float64)))
@@ -711,7 +767,12 @@ def main():
     ap.add_argument("--proximity", action="store_true", help="config 1: folded sheet with the stencils of the proximity producer (collide.py)")
     ap.add_argument("--no-strong", action="store_true", help="skip the BASELINE config 4 (2048^2) strong-scaling measurement beside the headline")
     ap.add_argument("--no-arbiter", action="store_true", help="skip the FP64 arbiter of the in-run value parity (a few seconds per million vertices)")
+    ap.add_argument("--cpu-leg-child", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-leg-port", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_leg_child:
+        cpu_leg_child(args.cpu_leg_child, args.steps, args.warmup, int(os.environ.get("MAS_BENCH_THREADS", host_threads())), args.cpu_leg_port)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -149,11 +149,27 @@ __device__ __forceinline__ void store_operand_row(float* __restrict__ hiBuf, flo
 	}
 }
 
+// What the NEXT fine bank of this CTA will gather, so that the pivot warp (idle but for sixteen elimination steps per panel)
+// can pull it into L2 while this system is being inverted: the gather is three dependent global round trips (s2o -> CSR
+// range -> neighbour indices -> blocks; 10 k cycles per bank when they all go to HBM).  The chain is walked in stages, one
+// per panel, each consuming what the previous stage loaded a few thousand cycles earlier: the warp never waits on memory.
+struct TcPrefetch
+{
+	const int* s2o = nullptr;
+	const int* adjStart = nullptr;
+	const int* ranges = nullptr;
+	const int* adjIdx = nullptr;
+	const float* offdiag = nullptr;
+	const float* diag = nullptr;
+	int nv = 0, bank = -1;            // bank < 0: nothing to prefetch
+};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // In: s.A holds the assembled 96x96 system (row stride kLdP), all threads past the barrier that completed it.
 // Out: s.packed holds the packed inverse (lane-slot layout, mas_internal.h), all threads past a barrier.
 // pos96[r * 96 + c], r >= c: packed position of symmetric element (r, c).  `parity`: phase of s.bar, carried across systems.
 __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint32_t& parity, const unsigned short* __restrict__ pos96,
-	int* __restrict__ errFlag, PhaseClock& pc)
+	int* __restrict__ errFlag, PhaseClock& pc, const TcPrefetch pf = TcPrefetch())
 {
 	// the warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role branches below uniform
 	// (from threadIdx alone it cannot, and wraps every shuffle inside `if (warp == 3)` in a convergence sequence)
@@ -198,6 +214,7 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 	}
 	pc.mark(3);
 
+	int pfOv = 0, pfE0 = 0, pfE1 = 0, pfSrc = 0;       // prefetch state of the pivot warp
 #pragma unroll 1
 	for (int K = 0; K < 6; ++K)
 	{
@@ -240,6 +257,30 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 		if (warp == 3)
 		{
 			invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
+			// staged prefetch of the next bank's inputs (lane = vertex), see TcPrefetch
+			const int vn = pf.bank * 32 + lane;
+			if (pf.bank >= 0 && vn < pf.nv)
+			{
+				if (K == 0)
+				{
+					pfOv = pf.s2o[vn];
+					pfE0 = pf.adjStart[vn];
+					pfE1 = pf.adjStart[vn + 1];
+				}
+				else if (K == 1)
+				{
+					pfSrc = pf.ranges[pfOv];
+					prefetch_l2(pf.adjIdx + pfE0);
+					prefetch_l2(pf.adjIdx + pfE1 - 1);
+					prefetch_l2(pf.diag + 9 * (size_t)pfOv);
+				}
+				else if (K == 2)
+				{
+					const char* first = reinterpret_cast<const char*>(pf.offdiag + 9 * (size_t)pfSrc);
+					const int bytes = 36 * (pfE1 - pfE0);
+					for (int off = 0; off < bytes + 127; off += 128) prefetch_l2(first + (off < bytes ? off : bytes - 1));
+				}
+			}
 		}
 		tc::fence_async_smem();
 		tc::fence_before_sync();
