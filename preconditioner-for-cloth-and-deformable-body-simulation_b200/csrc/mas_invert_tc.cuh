@@ -257,7 +257,32 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 		if (warp == 3)
 		{
 			invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
-			// staged prefetch of the next bank's inputs (lane = vertex), see TcPrefetch
+		}
+		tc::fence_async_smem();
+		tc::fence_before_sync();
+		__syncthreads();
+		pc.mark(6);
+		const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
+		if (t == 96)
+		{
+			// T[:, K] = C P^T (3xTF32, small terms first; the first MMA overwrites the column block)
+			tc::fence_after_sync();
+			constexpr uint32_t idP = tc::idesc_tf32(128, 16);
+			const uint32_t pH = tc::smem_addr(s.pHi), pL = tc::smem_addr(s.pLo);
+#pragma unroll
+			for (int ks = 0; ks < 2; ++ks)
+			{
+				const uint32_t off = ks * 2 * tc::kLbo;
+				tc::mma_tf32(colK, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, ks);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pL + off, tc::kLbo, tc::kSbo), idP, 1u);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, 1u);
+			}
+			tc::mma_commit(&s.bar);
+		}
+		if (warp == 3)
+		{
+			// staged prefetch of the next bank's inputs (lane = vertex), see TcPrefetch; here the pivot warp has nothing else to do
+			// until the product C P^T completes
 			const int vn = pf.bank * 32 + lane;
 			if (pf.bank >= 0 && vn < pf.nv)
 			{
@@ -281,27 +306,6 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 					for (int off = 0; off < bytes + 127; off += 128) prefetch_l2(first + (off < bytes ? off : bytes - 1));
 				}
 			}
-		}
-		tc::fence_async_smem();
-		tc::fence_before_sync();
-		__syncthreads();
-		pc.mark(6);
-		const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
-		if (t == 96)
-		{
-			// T[:, K] = C P^T (3xTF32, small terms first; the first MMA overwrites the column block)
-			tc::fence_after_sync();
-			constexpr uint32_t idP = tc::idesc_tf32(128, 16);
-			const uint32_t pH = tc::smem_addr(s.pHi), pL = tc::smem_addr(s.pLo);
-#pragma unroll
-			for (int ks = 0; ks < 2; ++ks)
-			{
-				const uint32_t off = ks * 2 * tc::kLbo;
-				tc::mma_tf32(colK, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, ks);
-				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pL + off, tc::kLbo, tc::kSbo), idP, 1u);
-				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, 1u);
-			}
-			tc::mma_commit(&s.bar);
 		}
 		if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
 		parity ^= 1u;
