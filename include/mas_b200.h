@@ -213,7 +213,8 @@ int mas_peer_attach(mas_handle_t h, const void* handles, void* const* pointers);
 /* Caller-side harness (the reference ships no solver): preconditioned conjugate gradients for A x = b with
  * everything resident on the GPU.  A is given exactly as PreparePreconditioner receives it (original vertex order):
  * diagonal[nv] and csrOffDiagonals[nnz] 36-byte column-major blocks, csrRanges[nv+1] / csrIdx[nnz] the adjacency CSR
- * (h:51 m_neighbours).  b, x: 16-byte xyzw vectors, x0 = 0.  Stops when ||r||_2 / ||b||_2 < relTol or after maxIter
+ * (h:51 m_neighbours); the Hessians of the collision stencils of the last mas_prepare, stiff (w (x) w) (x) (d d^T) per stencil
+ * (cpp:1201-1227) — which the preconditioner was built for — are part of A and applied matrix-free.  b, x: 16-byte xyzw vectors, x0 = 0.  Stops when ||r||_2 / ||b||_2 < relTol or after maxIter
  * iterations; dot products in FP64.  usePreconditioner = 0 runs plain CG (z = r).  Requires mas_prepare when
  * usePreconditioner != 0.  Single-GPU contexts only. */
 int mas_pcg_solve(mas_handle_t h, const float* diagonal, const float* csrOffDiagonals, const int* csrRanges, const int* csrIdx,

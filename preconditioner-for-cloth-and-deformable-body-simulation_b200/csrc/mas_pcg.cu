@@ -10,6 +10,9 @@
 // One iteration = 4 launches + the apply's own launches, captured once in a CUDA graph and replayed; the stopping test is
 // evaluated on the device (a flag turns the remaining launches of a batch into no-ops), so the host synchronises once per
 // batch of iterations, not once per iteration.
+//   A includes the collision Hessians of the stencils of the last PreparePreconditioner (what the preconditioner was built
+//   for, cpp:1164-1227): stiff (w (x) w) (x) (d d^T) per stencil, applied matrix-free by stencil_spmv (one thread per stencil,
+//   float atomics into Ap: with stencils the summation order, and with it the last bit of the iterates, varies from run to run).
 //   spmv_dot      Ap = A p, partial sums of p.Ap.  A is converted once per solve to a sliced-ELL layout (32-row slices,
 //                 every (block slot, entry) of a slice is 32 consecutive floats): lane = row, all loads coalesced, nine
 //                 FMAs per eleven loads and no cross-lane traffic (the CSR kernel it replaces staged blocks through
@@ -173,13 +176,47 @@ __global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __re
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(kPcgThreads) axpy_rr_kernel(float4* __restrict__ x, float4* __restrict__ r,
-	const float4* __restrict__ p, const float4* __restrict__ Ap, int nv, const double* __restrict__ pApPartials, int nPartials,
-	double* __restrict__ rrPartials, const volatile PcgState* st)
+// Ap += (sum of the collision Hessians) p and the matching part of p.Ap: stencil s contributes stiff (w (x) w) (x) (d d^T)
+// (PrepareCollisionHessian, cpp:1201-1227: OuterProduct(d, d stiff) weighted by w_a w_b for every vertex pair of the stencil),
+// i.e. alpha = stiff sum_k w_k (d . p_k),  Ap_k += w_k alpha d,  p.Ap += alpha^2 / stiff.  Stencil indices are original ids.
+__global__ void __launch_bounds__(kPcgThreads) stencil_spmv_kernel(const Stencil* __restrict__ stencils, int nStencil,
+	const float4* __restrict__ p, float4* __restrict__ Ap, double* __restrict__ partials, const volatile PcgState* st)
 {
 	__shared__ double sh[kPcgWarps];
 	if (st->done) return;
-	const double pAp = reduce_partials(pApPartials, nPartials, sh);
+	double dot = 0.0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nStencil; i += gridDim.x * blockDim.x)
+	{
+		const Stencil s = stencils[i];
+		float a = 0.f;
+		for (int k = 0; k < s.n; ++k)
+		{
+			const float4 q = p[s.index[k]];
+			a = fmaf(s.weight[k], fmaf(s.dir[0], q.x, fmaf(s.dir[1], q.y, s.dir[2] * q.z)), a);
+		}
+		const float alpha = s.stiff * a;
+		for (int k = 0; k < s.n; ++k)
+		{
+			const float w = s.weight[k] * alpha;
+			float* dst = reinterpret_cast<float*>(Ap + s.index[k]);
+			atomicAdd(dst + 0, w * s.dir[0]);
+			atomicAdd(dst + 1, w * s.dir[1]);
+			atomicAdd(dst + 2, w * s.dir[2]);
+		}
+		dot += (double)alpha * (double)a;
+	}
+	const double t = block_sum(dot, sh);
+	if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kPcgThreads) axpy_rr_kernel(float4* __restrict__ x, float4* __restrict__ r,
+	const float4* __restrict__ p, const float4* __restrict__ Ap, int nv, const double* __restrict__ pApPartials,
+	const double* __restrict__ pApStencilPartials, int nPartials, double* __restrict__ rrPartials, const volatile PcgState* st)
+{
+	__shared__ double sh[kPcgWarps];
+	if (st->done) return;
+	double pAp = reduce_partials(pApPartials, nPartials, sh);
+	if (pApStencilPartials) pAp += reduce_partials(pApStencilPartials, nPartials, sh);
 	const float alpha = (float)(st->rz / pAp);
 	double rr = 0.0;
 	const int stride = gridDim.x * blockDim.x;
@@ -312,11 +349,16 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (int rc = reserve(c, c->pcgZ, (size_t)nv)) return rc;
 	if (int rc = reserve(c, c->pcgP, (size_t)nv)) return rc;
 	if (int rc = reserve(c, c->pcgAp, (size_t)nv)) return rc;
-	if (int rc = reserve(c, c->pcgPartials, (size_t)3 * kMaxPartials)) return rc;
+	if (int rc = reserve(c, c->pcgPartials, (size_t)4 * kMaxPartials)) return rc;
 	if (int rc = reserve(c, c->pcgState, (size_t)sizeof(PcgState))) return rc;
 	double* pA = c->pcgPartials.p;
 	double* pRR = pA + kMaxPartials;
 	double* pRZ = pRR + kMaxPartials;
+	double* pS = pRZ + kMaxPartials;      // p.Ap, collision part
+	// the collision stencils of the last prepare belong to A (the preconditioner was built for A + their Hessians)
+	const int nStencil = c->prepared ? c->nStencil : 0;
+	int gridStencil = cdiv(nStencil, kPcgThreads);
+	if (gridStencil > kMaxPartials) gridStencil = kMaxPartials;
 	PcgState* state = reinterpret_cast<PcgState*>(c->pcgState.p);
 	float4 *r = c->pcgR.p, *z = usePrecond ? c->pcgZ.p : c->pcgR.p, *p = c->pcgP.p, *Ap = c->pcgAp.p;
 
@@ -344,7 +386,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		c->pcgEllIdx.p, c->pcgEllVal.p);
 
 	MAS_CUDA(c, cudaMemsetAsync(state, 0, sizeof(PcgState), st));
-	MAS_CUDA(c, cudaMemsetAsync(pA, 0, sizeof(double) * 3 * kMaxPartials, st));
+	MAS_CUDA(c, cudaMemsetAsync(pA, 0, sizeof(double) * 4 * kMaxPartials, st));
 	copy_b_kernel<<<cdiv(nv, 256), 256, 0, st>>>(b, r, x, nv);
 	auto precondition = [&]() -> int {
 		if (!usePrecond) return MAS_OK;
@@ -371,13 +413,15 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	{
 		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(diag, c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
 			nv, pA, state);
-		axpy_rr_kernel<<<grid, kPcgThreads, 0, cap>>>(x, r, p, Ap, nv, pA, nPart, pRR, state);
+		if (nStencil > 0)
+			stencil_spmv_kernel<<<gridStencil, kPcgThreads, 0, cap>>>(c->stencils.p, nStencil, p, Ap, pS, state);
+		axpy_rr_kernel<<<grid, kPcgThreads, 0, cap>>>(x, r, p, Ap, nv, pA, nStencil > 0 ? pS : nullptr, nPart, pRR, state);
 		c->applyLaunches = 0;
 		if (usePrecond) rc = apply_forked(c, r, z, cap);   // coarse chain concurrent with the head of the fine solve
 		dot_kernel<<<grid, kPcgThreads, 0, cap>>>(r, z, nv, pRZ, state);
 		update_p_kernel<<<grid, kPcgThreads, 0, cap>>>(p, z, nv, pRZ, pRR, nPart, tol2, 1, state);
 	}
-	c->pcgLaunchesPerIter = 4 + (usePrecond ? c->applyLaunches : 0);
+	c->pcgLaunchesPerIter = 4 + (nStencil > 0 ? 1 : 0) + (usePrecond ? c->applyLaunches : 0);
 	c->applyLaunches = savedLaunches;
 	cudaError_t e = cudaStreamEndCapture(cap, &graph);
 	c->stream = saved;

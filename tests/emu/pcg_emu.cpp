@@ -67,7 +67,7 @@ int main()
 		emu::launch(gridSpmv, kPcgThreads, [&] {
 			spmv_dot_kernel(diag.data(), sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data(), p.data(), Ap.data(), nv, pA, &state);
 		});
-		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(x.data(), r.data(), p.data(), Ap.data(), nv, pA, nPart, pRR, &state); });
+		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(x.data(), r.data(), p.data(), Ap.data(), nv, pA, nullptr, nPart, pRR, &state); });
 		emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
 		emu::launch(grid, kPcgThreads, [&] { update_p_kernel(p.data(), z, nv, pRZ, pRR, nPart, tol2, 1, &state); });
 	}
