@@ -361,8 +361,6 @@ def run_ours(args):
         g.set_option(1, args.variant)
     if args.invert_variant:
         g.set_option(8, args.invert_variant)       # MAS_OPT_INVERT_VARIANT: 0 tensor cores (default), 1 FP32 CUDA cores
-    if args.fused_chain is not None:
-        g.set_option(11, args.fused_chain)         # MAS_OPT_FUSED_CHAIN: 1 (default) one persistent kernel for the coarse chain
     p2p = False
     if world > 1:
         drv = pkg.partition.ShardedSchwarzPreconditioner(g)
@@ -763,7 +761,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="only the timed loop (for runs under ncu)")
     ap.add_argument("--variant", type=int, default=None, help="MAS_OPT_APPLY_VARIANT override (development sweeps)")
-    ap.add_argument("--fused-chain", type=int, default=None, help="MAS_OPT_FUSED_CHAIN override (1 = default: the coarse chain as one kernel)")
     ap.add_argument("--invert-variant", type=int, default=0, help="MAS_OPT_INVERT_VARIANT: 0 = tcgen05 tensor cores (default), 1 = FP32 CUDA cores")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use the NCCL all-reduce baseline instead of the peer-memory exchange")
     ap.add_argument("--cpu-pcg", action="store_true", help="also run the PCG solve on the host with the reference preconditioner")

@@ -112,12 +112,7 @@ enum
 	 * one without stencils keeps the clustering (levels, goingNext, coarse tables, shard cuts): it depends on the sorted
 	 * adjacency and the stencils only, so the rebuilt one would be identical bit for bit (verified on hardware).  Assembly
 	 * and inversion always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds.  0: always rebuild. */
-	MAS_OPT_CACHE_HIERARCHY = 10,
-	/* 1 (default): inside the apply graph the whole coarse chain (restriction of every level, peer exchange, coarse solves,
-	 * prolongation sum) is ONE persistent kernel of at most one CTA per SM with grid-wide barriers between its phases,
-	 * launched ahead of the concurrent level-0 solve.  0: one kernel per phase (the launch sequence the phase-split protocol
-	 * and the un-captured path always use).  Bit-identical z either way. */
-	MAS_OPT_FUSED_CHAIN = 11
+	MAS_OPT_CACHE_HIERARCHY = 10
 };
 
 /* mas_get_int keys */

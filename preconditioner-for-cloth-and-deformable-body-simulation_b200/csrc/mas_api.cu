@@ -170,7 +170,7 @@ static int peer_failed(Context* c)
 	}
 	if (code != 0u)
 	{
-		c->err = "apply: a grid barrier of the coarse-chain kernel timed out (results are invalid)";
+		c->err = "apply: a device-side wait timed out (results are invalid)";
 		return MAS_ERR_CUDA;
 	}
 	return MAS_OK;
@@ -182,7 +182,7 @@ static void free_all(Context* c)
 	close_peers(c);
 	if (c->peerErrHost) { cudaFreeHost(c->peerErrHost); c->peerErrHost = nullptr; c->peerErrDev = nullptr; }
 	unregister_host_ranges(c);
-	release(c->arena); release(c->cutInfo); release(c->chainBar);
+	release(c->arena); release(c->cutInfo);
 	release(c->positions); release(c->edges); release(c->faces); release(c->inStarts); release(c->inIdx);
 	release(c->aabb); release(c->code); release(c->codeSorted); release(c->s2o); release(c->o2s); release(c->iota);
 	release(c->adjStart); release(c->adjIdx); release(c->cubTemp);
@@ -238,17 +238,14 @@ int mas_create(mas_handle_t* out, int device)
 		cudaStreamCreateWithPriority(&c->sideB, cudaStreamNonBlocking, prLow);
 	}
 	// sticky error word of the apply kernels in page-locked, device-mapped host memory (the host sees a timed-out device-side
-	// wait without a device round trip) and the grid barrier of the fused coarse-chain kernel
+	// peer wait without a device round trip)
 	if (cudaHostAlloc((void**)&c->peerErrHost, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
-		cudaHostGetDevicePointer((void**)&c->peerErrDev, c->peerErrHost, 0) != cudaSuccess ||
-		cudaMalloc((void**)&c->chainBar.p, 2 * sizeof(unsigned)) != cudaSuccess || cudaMemset(c->chainBar.p, 0, 2 * sizeof(unsigned)) != cudaSuccess)
+		cudaHostGetDevicePointer((void**)&c->peerErrDev, c->peerErrHost, 0) != cudaSuccess)
 	{
 		delete c;
 		return MAS_ERR_CUDA;
 	}
 	*c->peerErrHost = 0u;
-	c->applyErrDev = c->peerErrDev;
-	c->chainBar.cap = 2;
 	*out = c;
 	return MAS_OK;
 }
@@ -298,7 +295,6 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
-	case MAS_OPT_FUSED_CHAIN: h->optFusedChain = value ? 1 : 0; break;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:

@@ -499,203 +499,6 @@ __global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int
 	zsum[i] = make_float4(z.x, z.y, z.z, 0.f);
 }
 
-#ifndef MAS_CPU_EMULATION
-// ---- the whole coarse chain in ONE kernel -------------------------------------------------------------------------------
-// restrict_fine -> [peer exchange] -> restriction of the coarse levels -> coarse solves -> prolong_sum as phases of one
-// persistent grid of at most one CTA per SM, separated by grid-wide barriers (a counter and a generation word in global
-// memory; every CTA is resident, the grid never exceeds the SM count).  As separate launches the chain is five to seven
-// dependent, latency-bound kernels whose CTAs moreover queue behind the not-yet-dispatched CTAs of the concurrent level-0
-// solve; that capped the concurrent "head" of the apply graph at one wave (27 us) under a chain of 31 us on one GPU and
-// 45 us on eight (weak-scaling efficiency 0.89).  One kernel, launched ahead of the head, is resident from the start: no
-// launch gaps, no dispatch queueing, and the head can be as long as the chain.  Same device functions, same order of every
-// floating-point sum as the separate kernels (which the phase-split protocol and the un-captured path still launch):
-// bit-identical results.
-struct ChainArgs
-{
-	const float4* r; const int* s2o; const int* goingNext; const float* packedCoarse;
-	float4 *coarseR, *coarseZ, *zsum;
-	int nv, nVC, numLevel;
-	int fineBegin, fineEnd;            // owned fine banks
-	int count[kMaxLevel + 1], begin[kMaxLevel + 1];   // nodes / first node id per level
-	int l1BankBegin, l1BankEnd;        // level-1 banks restricted here (own banks when the cuts are aligned, else all)
-	int firstTop;                      // levels >= firstTop are walked by block 0 alone (they hold a few hundred nodes)
-	int l1Begin, ownL1, topBegin, solved;   // coarse blocks solved by this rank: ownL1 level-1 blocks from l1Begin, then from topBegin
-	int psFirst, psLast, extraLevels, skipProlong;
-	int usePeers, l2x, peerFirst, peerCount;
-	PeerArgs pa;
-	unsigned* bar;                     // [0] arrivals, [1] generation
-	unsigned* error;                   // sticky error word (host-mapped): a barrier or peer wait timed out
-};
-
-__device__ __forceinline__ void chain_grid_sync(unsigned* bar, unsigned& gen, unsigned* error)
-{
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		__threadfence();
-		if (atomicAdd(&bar[0], 1u) == gridDim.x - 1)
-		{
-			bar[0] = 0u;
-			__threadfence();
-			asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
-		}
-		else
-		{
-			const long long t0 = clock64();
-			unsigned g;
-			do
-			{
-				asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
-				if (g != gen) break;
-				if (clock64() - t0 > 4000000000ll) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(error), "r"(2u) : "memory"); break; }
-			} while (true);
-		}
-		__threadfence();
-	}
-	gen += 1u;
-	__syncthreads();
-}
-
-__global__ void __launch_bounds__(kApplyThreads) coarse_chain_kernel(const ChainArgs a)
-{
-	__shared__ float part[2][3][32][3];
-	__shared__ int peersOk;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned gen = *reinterpret_cast<volatile unsigned*>(a.bar + 1);
-	const unsigned want = a.usePeers ? *reinterpret_cast<volatile unsigned*>(a.pa.epoch) + 1u : 0u;
-	float4* sendBuf = a.usePeers ? a.pa.send[a.pa.rank] + (unsigned long long)(want & 1u) * a.pa.cap : nullptr;
-
-	// BuildResidualHierarchy, level 0 -> 1 (cpp:1558-1574)
-	{
-		const int warpsNeeded = (a.fineEnd - a.fineBegin + kRestrictBanks - 1) / kRestrictBanks;
-		for (int w = blockIdx.x * kWarpsPerCta + warp; w < warpsNeeded; w += gridDim.x * kWarpsPerCta)
-			restrict_fine_warp(a.fineBegin + w * kRestrictBanks, lane, a.r, a.s2o, a.goingNext, a.nv, a.nVC, a.fineEnd, a.coarseR,
-				(a.usePeers && !a.l2x) ? sendBuf : nullptr);
-	}
-	chain_grid_sync(a.bar, gen, a.error);
-
-	// the all-gather of the other ranks' coarse residuals over peer memory (see gather_peers_kernel): level 1 when the cuts
-	// are not aligned, level 2 (after this rank's own level-1 banks have been restricted) when they are
-	auto exchange = [&]() {
-		if (blockIdx.x == 0 && (int)threadIdx.x < a.pa.world)
-			asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.pa.flags[threadIdx.x] + a.pa.rank), "r"(want) : "memory");
-		if (threadIdx.x == 0) peersOk = 1;
-		__syncthreads();
-		if ((int)threadIdx.x < a.pa.world)
-		{
-			const unsigned* f = a.pa.flags[a.pa.rank] + threadIdx.x;
-			const long long t0 = clock64();
-			while ((int)(ld_acquire_sys(f) - want) < 0)
-			{
-				if (clock64() - t0 > 4000000000ll)
-				{
-					peersOk = 0;
-					asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a.error), "r"(1u) : "memory");
-					break;
-				}
-				__nanosleep(32);
-			}
-		}
-		__syncthreads();
-		if (peersOk)
-		{
-			const unsigned long long off = (unsigned long long)(want & 1u) * a.pa.cap;
-			const int stride = gridDim.x * blockDim.x;
-			for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < a.peerCount; base += kGatherPerThread * stride)
-			{
-				const float4* src[kGatherPerThread];
-				float4 v[kGatherPerThread];
-#pragma unroll
-				for (int k = 0; k < kGatherPerThread; ++k)
-				{
-					const int i = a.peerFirst + base + k * stride;
-					src[k] = nullptr;
-					if (base + k * stride < a.peerCount)
-					{
-						int q = 0;
-						while (q + 1 < a.pa.world && i >= a.pa.sliceBegin[q + 1]) ++q;
-						if (q != a.pa.rank) src[k] = a.pa.send[q] + off + i;
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < kGatherPerThread; ++k)
-					if (src[k]) v[k] = __ldcg(src[k]);
-#pragma unroll
-				for (int k = 0; k < kGatherPerThread; ++k)
-					if (src[k]) a.coarseR[a.peerFirst + base + k * stride] = v[k];
-			}
-		}
-		chain_grid_sync(a.bar, gen, a.error);
-		if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(a.pa.epoch) = want;   // everybody has read it
-	};
-	if (a.usePeers && !a.l2x) exchange();
-
-	// BuildResidualHierarchy, levels >= 1 (cpp:1577-1591): large levels on the whole grid, the small top by block 0 alone
-	for (int level = 1; level + 1 < a.numLevel && level < a.firstTop; ++level)
-	{
-		const bool own = level == 1;                 // level 1: the banks this rank is responsible for
-		const int bb = own ? a.l1BankBegin : 0, be = own ? a.l1BankEnd : (a.count[level] + 31) >> 5;
-		for (int bank = bb + blockIdx.x * kWarpsPerCta + warp; bank < be; bank += gridDim.x * kWarpsPerCta)
-		{
-			if (bank * 32 >= a.count[level]) break;
-			const int local = bank * 32 + lane;
-			float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (local < a.count[level]) rv = a.coarseR[a.begin[level] - a.nVC + local];
-			restrict_bank(a.goingNext, a.begin[level], a.count[level], bank, a.nVC, a.coarseR, lane, rv,
-				(own && a.usePeers && a.l2x) ? sendBuf : nullptr);
-		}
-		chain_grid_sync(a.bar, gen, a.error);
-		if (own && a.usePeers && a.l2x) exchange();
-	}
-	if (blockIdx.x == 0)
-	{
-		for (int level = a.firstTop; level + 1 < a.numLevel; ++level)
-		{
-			const int banks = (a.count[level] + 31) >> 5;
-			for (int bank = warp; bank < banks; bank += kWarpsPerCta)
-			{
-				const int local = bank * 32 + lane;
-				float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (local < a.count[level]) rv = a.coarseR[a.begin[level] - a.nVC + local];
-				restrict_bank(a.goingNext, a.begin[level], a.count[level], bank, a.nVC, a.coarseR, lane, rv);
-			}
-			__threadfence_block();
-			__syncthreads();
-		}
-	}
-	if (a.firstTop + 1 < a.numLevel) chain_grid_sync(a.bar, gen, a.error);
-
-	// SchwarzLocalXSym on the coarse blocks (cpp:1600-1696): two blocks per CTA pass, four warps each
-	for (int base = 2 * blockIdx.x; base < a.solved; base += 2 * gridDim.x)
-	{
-		const int g = warp >> 2, w4 = warp & 3, i = base + g;
-		const bool live = i < a.solved;
-		const int blk = i < a.ownL1 ? a.l1Begin + i : a.topBegin + (i - a.ownL1);
-		Vec3 y = { 0.f, 0.f, 0.f };
-		if (live) y = solve_coarse_part(a.packedCoarse, a.coarseR, blk, lane, w4, part[g]);
-		__syncthreads();
-		if (live) solve_coarse_sum(y, a.coarseZ, blk, lane, w4, part[g]);
-		__syncthreads();
-	}
-	if (a.skipProlong) return;
-	chain_grid_sync(a.bar, gen, a.error);
-
-	// what CollectFinalZ adds below every level-1 node (prolong_sum_kernel)
-	for (int i = a.psFirst + blockIdx.x * blockDim.x + threadIdx.x; i < a.psLast; i += gridDim.x * blockDim.x)
-	{
-		int node = a.begin[1] + i;
-		float4 z = a.coarseZ[node - a.nVC];
-		for (int l = 0; l < a.extraLevels; ++l)
-		{
-			node = a.goingNext[node];
-			const float4 u = a.coarseZ[node - a.nVC];
-			z.x += u.x; z.y += u.y; z.z += u.z;
-		}
-		a.zsum[i] = make_float4(z.x, z.y, z.z, 0.f);
-	}
-}
-#endif  // MAS_CPU_EMULATION
-
 // SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ.
 // addCoarse = 0: the coarse levels are not ready (or absent); z holds the level-0 part only.
 // One warp per bank.
@@ -924,58 +727,6 @@ int apply_end(Context* c, const float4* r, float4* z)
 	return MAS_OK;
 }
 
-// the coarse chain as one kernel (see coarse_chain_kernel); replaces apply_begin + launch_coarse inside the apply graph
-static int launch_chain(Context* c, cudaStream_t st, const float4* r, bool skipProlongSum)
-{
-	if (c->numLevel < 2) return MAS_OK;
-	ChainArgs a;
-	a.r = r; a.s2o = c->s2o.p; a.goingNext = c->goingNext.p;
-	a.packedCoarse = c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri;
-	a.coarseR = c->coarseR.p; a.coarseZ = c->coarseZ.p; a.zsum = c->coarseZsum.p;
-	a.nv = c->nv; a.nVC = c->nVC; a.numLevel = c->numLevel;
-	a.fineBegin = c->ownFineBegin; a.fineEnd = c->ownFineEnd;
-	for (int l = 0; l <= kMaxLevel; ++l) { a.count[l] = 0; a.begin[l] = 0; }
-	for (int l = 1; l <= c->numLevel && l <= kMaxLevel; ++l) { a.count[l] = c->levelSize[l][0]; a.begin[l] = c->levelSize[l][1]; }
-	const int cnt1 = c->levelSize[1][0];
-	const bool peers = use_peers(c), l2x = exchange_level2(c);
-	a.usePeers = (peers && !(l2x && c->numLevel < 3)) ? 1 : 0;
-	a.l2x = l2x ? 1 : 0;
-	a.l1BankBegin = l2x ? c->l1BlockBegin : 0;
-	a.l1BankEnd = l2x ? c->l1BlockEnd : cdiv(cnt1, 32);
-	// block 0 alone walks the levels that hold at most 2,048 nodes (and, on small single-GPU meshes, level 1 as well)
-	a.firstTop = 1;
-	while (a.firstTop + 1 < c->numLevel && (c->levelSize[a.firstTop][0] > 2048 || (a.firstTop == 1 && (c->world > 1 || cnt1 > 512)))) a.firstTop += 1;
-	const int nCoarseBlocks = c->nCoarseNodes / 32;
-	a.l1Begin = c->l1BlockBegin; a.ownL1 = c->l1BlockEnd - c->l1BlockBegin; a.topBegin = c->nL1Blocks;
-	a.solved = a.ownL1 + (nCoarseBlocks - c->nL1Blocks);
-	a.psFirst = c->world > 1 ? c->l1Slice[c->rank] : 0;
-	a.psLast = c->world > 1 ? c->l1Slice[c->rank + 1] : cnt1;
-	a.extraLevels = prolonged_top(c) - 2;
-	a.skipProlong = skipProlongSum ? 1 : 0;
-	if (a.usePeers)
-	{
-		a.pa = peer_args(c);
-		a.peerFirst = l2x ? c->levelSize[2][1] - c->nVC : c->levelSize[1][1] - c->nVC;
-		a.peerCount = l2x ? c->levelSize[2][0] : cnt1;
-	}
-	else
-	{
-		a.peerFirst = a.peerCount = 0;
-		for (int q = 0; q < kMaxWorld; ++q) { a.pa.send[q] = nullptr; a.pa.flags[q] = nullptr; }
-		a.pa.world = 1; a.pa.rank = 0; a.pa.epoch = nullptr; a.pa.cap = 0;
-	}
-	a.bar = c->chainBar.p;             // allocated and zeroed by mas_create
-	a.error = c->applyErrDev;
-	// one CTA per SM at most (all resident: the grid barrier needs that), fewer when there is little to do
-	int work = cdiv(cdiv(c->ownFineEnd - c->ownFineBegin, kRestrictBanks), kWarpsPerCta);
-	if (cdiv(a.solved, 2) > work) work = cdiv(a.solved, 2);
-	int grid = work < c->smCount ? work : c->smCount;
-	if (grid < 1) grid = 1;
-	coarse_chain_kernel<<<grid, kApplyThreads, 0, st>>>(a);
-	c->applyLaunches += 1;
-	return MAS_OK;
-}
-
 // Whole apply as a two-branch capture (graph path; single GPU, or sharded with the peer-memory exchange).  `st` is the capturing origin stream; side streams and
 // events belong to the context.  headBanks fine banks are solved concurrently with the coarse chain.
 int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
@@ -996,15 +747,17 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 			const long long ownVerts = 32ll * ownBanks;
 			head = (int)(2400 + 8 * ownVerts / 2000);
 			if (use_peers(c)) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
-			if (c->optFusedChain && use_peers(c)) head += 1500 * (c->world > 4 ? 2 : 1);   // the wait absorbs the launch skew of the ranks
 		}
 		// The CTA dispatcher works through grids in launch order, and stream / node priority does not let a later grid overtake
 		// the not-yet-dispatched CTAs of an earlier one (measured: beside a head of more than one wave, 148 x 8 CTAs, every
 		// chain kernel waited 20-26 us until the head's last CTA had been dispatched).  The head therefore never exceeds one
 		// wave minus room for the chain's own CTAs: it is resident in full right away and the chain is dispatched beside it.
-		// (with the chain fused into one kernel, launched ahead of the head and resident from the start, there is no such limit)
+		// (Round 2 also measured the whole chain as ONE persistent kernel with grid barriers, launched ahead of the head: it
+		// removes the dispatch queueing and the launch gaps, but with at most one CTA per SM its restriction and solve phases
+		// lose their parallelism and its resident CTAs take registers from the streaming kernel: 117.0 against 104.5 us at 1M
+		// vertices, 37.2 / 30.5 us at 262k, 12.4 / 10.4 us at 4k; profiles/r02_fused_coarse_chain_kernel_measurement.txt.  Removed.)
 		const int cap = (c->smCount * 8 - 80) * kWarpsPerCta;
-		if (!c->optFusedChain && head > cap) head = cap;
+		if (head > cap) head = cap;
 		head = (head + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
 		if (head > ownBanks) head = ownBanks;
 	}
@@ -1023,16 +776,9 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 	const bool walk = c->world == 1 && head == ownBanks;
 	MAS_CUDA(c, cudaEventRecord(c->evFork, st));
 	MAS_CUDA(c, cudaStreamWaitEvent(c->sideA, c->evFork, 0));
-	if (c->optFusedChain)
+	launch_fine(c, c->sideA, r, z, b0, b1, 0);                      // level-0 part only, no coarse data needed
+	MAS_CUDA(c, cudaEventRecord(c->evHead, c->sideA));
 	{
-		if (int rc = launch_chain(c, st, r, walk)) return rc;       // first: its CTAs are resident before the head fills the SMs
-		launch_fine(c, c->sideA, r, z, b0, b1, 0);                  // level-0 part only, no coarse data needed
-		MAS_CUDA(c, cudaEventRecord(c->evHead, c->sideA));
-	}
-	else
-	{
-		launch_fine(c, c->sideA, r, z, b0, b1, 0);
-		MAS_CUDA(c, cudaEventRecord(c->evHead, c->sideA));
 		cudaStream_t saved = c->stream;
 		c->stream = st;
 		int rc = apply_begin(c, r);

@@ -99,7 +99,6 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 0: tcgen05 tensor-core inversion (3xTF32 block Gauss-Jordan); 1: FP32 CUDA-core blocked LDL^T
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
-	int optFusedChain = 1;       // 1: the apply graph runs the whole coarse chain as ONE persistent kernel (coarse_chain_kernel)
 	int optCacheHierarchy = 1;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
 	bool hierarchyCached = false;   // the hierarchy in this context was built without stencils for the current ordering / options
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight
@@ -185,10 +184,8 @@ struct Context
 	bool peerOpened[16] = {};         // opened through cudaIpcOpenMemHandle (must be closed)
 	bool p2p = false;
 	bool phaseSplit = false;          // inside mas_apply_begin / mas_apply_end: the caller does the exchange, peers are ignored
-	unsigned* peerErrHost = nullptr;  // page-locked, device-mapped word: 1 = a peer wait timed out, 2 = a grid barrier of the chain kernel (sticky)
+	unsigned* peerErrHost = nullptr;  // page-locked, device-mapped word (allocated by mas_create): 1 = a peer wait timed out (sticky)
 	unsigned* peerErrDev = nullptr;   // its device address
-	unsigned* applyErrDev = nullptr;  // = peerErrDev (allocated by mas_create for every context)
-	DevBuf<unsigned> chainBar;        // grid barrier of coarse_chain_kernel: [0] arrivals, [1] generation
 
 	// partition (fine banks owned by this rank)
 	int ownFineBegin = 0, ownFineEnd = 0;
