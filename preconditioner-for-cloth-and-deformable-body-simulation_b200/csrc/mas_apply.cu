@@ -502,13 +502,10 @@ __global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int
 // SchwarzLocalXSym on level 0 fused with the level-0 gather of BuildResidualHierarchy and with CollectFinalZ.
 // addCoarse = 0: the coarse levels are not ready (or absent); z holds the level-0 part only.
 // One warp per bank.
-__global__ void __launch_bounds__(kApplyThreads, 8) solve_fine_kernel(const float* __restrict__ packed,
-	const float4* __restrict__ r, const int* __restrict__ s2o, const int* __restrict__ goingNext,
-	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int packedBankBase, int addCoarse, float4* __restrict__ z)
+__device__ __forceinline__ void solve_fine_bank(const float* __restrict__ packed, const float4* __restrict__ r, const int* __restrict__ s2o,
+	const int* __restrict__ goingNext, const float4* __restrict__ zsum, int nv, int nVC, int bank, int packedBankBase, int addCoarse,
+	float4* __restrict__ z, const int lane)
 {
-	const int lane = threadIdx.x & 31;
-	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-	if (bank >= bankEnd) return;
 	const int v = bank * 32 + lane;
 	const bool live = v < nv;
 	int ov = 0, parent = 0;
@@ -530,6 +527,16 @@ __global__ void __launch_bounds__(kApplyThreads, 8) solve_fine_kernel(const floa
 		}
 		z[ov] = make_float4(y.x, y.y, y.z, 0.f);
 	}
+}
+
+__global__ void __launch_bounds__(kApplyThreads, 8) solve_fine_kernel(const float* __restrict__ packed,
+	const float4* __restrict__ r, const int* __restrict__ s2o, const int* __restrict__ goingNext,
+	const float4* __restrict__ zsum, int nv, int nVC, int bankBegin, int bankEnd, int packedBankBase, int addCoarse, float4* __restrict__ z)
+{
+	const int lane = threadIdx.x & 31;
+	const int bank = bankBegin + blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+	if (bank >= bankEnd) return;
+	solve_fine_bank(packed, r, s2o, goingNext, zsum, nv, nVC, bank, packedBankBase, addCoarse, z, lane);
 }
 
 // z += prolonged coarse solutions for the fine banks solved with addCoarse = 0
@@ -733,7 +740,7 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 {
 	const int top = prolonged_top(c);
 	const int ownBanks = c->ownFineEnd - c->ownFineBegin;
-	int head = 0;
+	int head = 0, headChunk = 1 << 30;
 	if (top >= 2 && c->optApplyVariant != 0)
 	{
 		if (c->optApplyVariant > 0)
@@ -756,8 +763,10 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		// removes the dispatch queueing and the launch gaps, but with at most one CTA per SM its restriction and solve phases
 		// lose their parallelism and its resident CTAs take registers from the streaming kernel: 117.0 against 104.5 us at 1M
 		// vertices, 37.2 / 30.5 us at 262k, 12.4 / 10.4 us at 4k; profiles/r02_fused_coarse_chain_kernel_measurement.txt.  Removed.)
-		const int cap = (c->smCount * 8 - 80) * kWarpsPerCta;
-		if (head > cap) head = cap;
+		// A head that has to cover a longer chain (sharded contexts: the peer exchange is on it) is launched as SEVERAL one-wave
+		// kernels one after the other on the side stream: each is dispatched in full the moment its predecessor has drained, so
+		// a chain kernel never finds undispatched head CTAs ahead of it.
+		headChunk = (c->smCount * 8 - 80) * kWarpsPerCta;
 		head = (head + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
 		if (head > ownBanks) head = ownBanks;
 	}
@@ -776,7 +785,8 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 	const bool walk = c->world == 1 && head == ownBanks;
 	MAS_CUDA(c, cudaEventRecord(c->evFork, st));
 	MAS_CUDA(c, cudaStreamWaitEvent(c->sideA, c->evFork, 0));
-	launch_fine(c, c->sideA, r, z, b0, b1, 0);                      // level-0 part only, no coarse data needed
+	for (int hb = b0; hb < b1; hb += headChunk)                      // level-0 part only, no coarse data needed
+		launch_fine(c, c->sideA, r, z, hb, hb + headChunk < b1 ? hb + headChunk : b1, 0);
 	MAS_CUDA(c, cudaEventRecord(c->evHead, c->sideA));
 	{
 		cudaStream_t saved = c->stream;
