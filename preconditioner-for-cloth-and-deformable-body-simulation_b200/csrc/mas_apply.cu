@@ -749,11 +749,13 @@ int apply_forked(Context* c, const float4* r, float4* z, cudaStream_t st)
 		{
 			// auto: as many banks as stream in the time the coarse chain takes.  The chain costs a fixed latency (five
 			// dependent launches, the peer wait), the level-0 restriction of the owned vertices and the coarse solves above them
-			// (level 1 is partitioned like the fine banks); ~330 banks stream per microsecond.  Fitted on the 1M-vertex sweep
-			// (optimum 6,500 banks).
+			// (level 1 is partitioned like the fine banks), all of it slowed by the streaming kernel it shares HBM with; ~330 banks
+			// stream per microsecond.  Fitted on sweeps at 1M vertices per GPU (optimum ~45 % of the banks on 1 and 2 GPUs:
+			// profiles/r02_head_sweep.txt; the round-1 fit, 2400 + 0.004 ownVerts, was made under the one-wave limit).
 			const long long ownVerts = 32ll * ownBanks;
-			head = (int)(2400 + 8 * ownVerts / 2000);
-			if (use_peers(c)) head += 3600;   // signal + peer wait + pull over NVLink: ~11 us more on the chain (2-GPU timeline)
+			head = (int)(2400 + 23 * ownVerts / 2000);
+			if (head > 15000) head = 15000;   // beyond ~1M vertices the chain grows little while every extra one-wave kernel costs a bubble (4.2M: 427 us at 15 %, 445 us at 38 %)
+			if (use_peers(c)) head += 1500;   // signal + peer wait + pull over NVLink
 		}
 		// The CTA dispatcher works through grids in launch order, and stream / node priority does not let a later grid overtake
 		// the not-yet-dispatched CTAs of an earlier one (measured: beside a head of more than one wave, 148 x 8 CTAs, every
