@@ -112,7 +112,13 @@ enum
 	 * one without stencils keeps the clustering (levels, goingNext, coarse tables, shard cuts): it depends on the sorted
 	 * adjacency and the stencils only, so the rebuilt one would be identical bit for bit (verified on hardware).  Assembly
 	 * and inversion always run.  A prepare with stencils, a re-sort or MAS_OPT_ALIGN_CUTS rebuilds.  0: always rebuild. */
-	MAS_OPT_CACHE_HIERARCHY = 10
+	MAS_OPT_CACHE_HIERARCHY = 10,
+	/* Sharded apply over peer memory, default 0.  The kernel that publishes a rank's coarse residuals stores its arrival flags
+	 * with st.relaxed.sys right after the kernel that wrote the payload has finished (the payload then sits in this GPU's L2,
+	 * the point of coherence for reads arriving over NVLink).  1: a system-scope fence precedes the flag stores, which is what
+	 * the PTX memory model guarantees between GPUs (kernel boundaries order at device scope); it costs a MEMBAR.SYS on the
+	 * latency-bound chain.  Bit-identical results either way on current NVLink hardware. */
+	MAS_OPT_STRICT_PUBLISH = 11
 };
 
 /* mas_get_int keys */

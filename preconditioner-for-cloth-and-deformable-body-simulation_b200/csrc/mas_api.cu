@@ -295,6 +295,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_TIME_KERNELS: h->optTimeKernels = value ? 1 : 0; break;
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
+	case MAS_OPT_STRICT_PUBLISH: h->optStrictPublish = value ? 1 : 0; break;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:

@@ -238,6 +238,7 @@ struct PeerArgs
 	unsigned* error;              // local sticky error flag (peer wait timed out)
 	unsigned long long cap;       // float4 elements per send buffer
 	int world, rank;
+	int strictPublish;            // MAS_OPT_STRICT_PUBLISH: system-scope fence before the flag stores
 };
 
 #ifndef MAS_CPU_EMULATION   // the peer exchange needs several GPUs: not part of the host emulation
@@ -264,7 +265,12 @@ __global__ void __launch_bounds__(256) gather_peers_kernel(PeerArgs pa, int firs
 	__shared__ int ok;
 	const unsigned want = *reinterpret_cast<volatile unsigned*>(pa.epoch) + 1u;
 	if (blockIdx.x == 0 && (int)threadIdx.x < pa.world)
+	{
+		// strict mode: order the payload (written by the previous kernel) before the flag at SYSTEM scope, as the PTX memory
+		// model asks for between GPUs; the default relies on the kernel boundary having put the payload into this GPU's L2
+		if (pa.strictPublish) __threadfence_system();
 		asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(pa.flags[threadIdx.x] + pa.rank), "r"(want) : "memory");
+	}
 	if (threadIdx.x == 0) ok = 1;
 	__syncthreads();
 	if ((int)threadIdx.x < pa.world)
@@ -607,6 +613,7 @@ static PeerArgs peer_args(const Context* c)
 	pa.cap = c->arenaCap;
 	pa.world = c->world;
 	pa.rank = c->rank;
+	pa.strictPublish = c->optStrictPublish;
 	return pa;
 }
 

@@ -99,6 +99,7 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 0: tcgen05 tensor-core inversion (3xTF32 block Gauss-Jordan); 1: FP32 CUDA-core blocked LDL^T
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
+	int optStrictPublish = 0;    // 1: system-scope fence before the peer flag stores of the sharded apply
 	int optCacheHierarchy = 1;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare
 	bool hierarchyCached = false;   // the hierarchy in this context was built without stencils for the current ordering / options
 	int optRegisterHost = 0;     // host-pointer apply: page-lock the caller's pageable r / z in place (cudaHostRegister) on first sight

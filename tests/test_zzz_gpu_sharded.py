@@ -146,6 +146,8 @@ def test_peer_memory_exchange_in_one_process(name, world, align, pkg, synth):
 
     for g in shards:
         g.peer_attach(pointers=arenas)
+        if align == 0:
+            g.set_option(11, 1)                            # MAS_OPT_STRICT_PUBLISH: system-scope fence before the flag stores
     zs = [torch.zeros_like(r) for _ in shards]             # same buffers every time: the apply graph is captured once per shard
     for rep in range(4):                                   # several applies: the double-buffered arenas and counters roll over
         for z in zs:
