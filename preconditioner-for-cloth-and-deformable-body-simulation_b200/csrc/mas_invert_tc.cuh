@@ -46,12 +46,7 @@ struct TcSmem
 	union
 	{
 		alignas(128) float A[kDof * kLdP];      // the assembled system, row stride 97 (assembly; read once into TMEM)
-		struct
-		{
-			TcOperands op;                      // panel operands (elimination)
-			float lookA[16 * kTcPs];            // look-ahead: (C P) rows of block K + 1 ...
-			float lookC[16 * kTcPs];            // ... and its C rows (the current values T[K+1, K+1] go to `piv`)
-		};
+		TcOperands op;                          // panel operands (elimination)
 		float packed[kTri];                     // packed inverse (epilogue)
 	};
 	alignas(16) float piv[16 * kTcPs];          // pivot block T[K, K]
@@ -91,61 +86,16 @@ __device__ __forceinline__ float rcp_newton(const float x)
 	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
 	return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
 }
-__device__ __forceinline__ void invert16_regs(float (&m)[8], float* __restrict__ P, float* __restrict__ pHi, float* __restrict__ pLo, const int lane);
-
 __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, float* __restrict__ P, float* __restrict__ pHi,
 	float* __restrict__ pLo, const int lane)
 {
-	const int row = lane & 15, c0 = 8 * (lane >> 4);
+	constexpr unsigned kAll = 0xffffffffu;
+	const int row = lane & 15, half = lane >> 4, c0 = 8 * half;
 	float m[8];
 	{
 		const float4 a = *reinterpret_cast<const float4*>(piv + row * kTcPs + c0), b = *reinterpret_cast<const float4*>(piv + row * kTcPs + c0 + 4);
 		m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w; m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
 	}
-	invert16_regs(m, P, pHi, pLo, lane);
-}
-
-// Look-ahead: the pivot block of panel K + 1 AFTER the update of panel K, formed on the CUDA cores while the tensor core does
-// that update: S[x][y] = T[x][y] - (C P)[x] . C[y] for x, y in block K + 1 (D = the current T[K+1, K+1], la = (C P) rows,
-// lc = C rows of block K + 1), then inverted as above.  The FP32 result differs from the 3xTF32 one in tensor memory by
-// rounding only, i.e. P is the exact inverse of a pivot block perturbed at the 1e-7 level: a backward error of the size every
-// other step has.
-__device__ __forceinline__ void invert16_lookahead(const float* __restrict__ D, const float* __restrict__ la, const float* __restrict__ lc,
-	float* __restrict__ P, float* __restrict__ pHi, float* __restrict__ pLo, const int lane)
-{
-	const int row = lane & 15, c0 = 8 * (lane >> 4);
-	float m[8], a[16];
-	{
-		const float4 d0 = *reinterpret_cast<const float4*>(D + row * kTcPs + c0), d1 = *reinterpret_cast<const float4*>(D + row * kTcPs + c0 + 4);
-		m[0] = d0.x; m[1] = d0.y; m[2] = d0.z; m[3] = d0.w; m[4] = d1.x; m[5] = d1.y; m[6] = d1.z; m[7] = d1.w;
-#pragma unroll
-		for (int q = 0; q < 4; ++q)
-		{
-			const float4 v = *reinterpret_cast<const float4*>(la + row * kTcPs + 4 * q);
-			a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-		}
-	}
-#pragma unroll
-	for (int c = 0; c < 8; ++c)
-	{
-		const float* cy = lc + (c0 + c) * kTcPs;
-#pragma unroll
-		for (int q = 0; q < 4; ++q)
-		{
-			const float4 v = *reinterpret_cast<const float4*>(cy + 4 * q);
-			m[c] = __fmaf_rn(-a[4 * q], v.x, m[c]);
-			m[c] = __fmaf_rn(-a[4 * q + 1], v.y, m[c]);
-			m[c] = __fmaf_rn(-a[4 * q + 2], v.z, m[c]);
-			m[c] = __fmaf_rn(-a[4 * q + 3], v.w, m[c]);
-		}
-	}
-	invert16_regs(m, P, pHi, pLo, lane);
-}
-
-__device__ __forceinline__ void invert16_regs(float (&m)[8], float* __restrict__ P, float* __restrict__ pHi, float* __restrict__ pLo, const int lane)
-{
-	constexpr unsigned kAll = 0xffffffffu;
-	const int row = lane & 15, half = lane >> 4, c0 = 8 * half;
 #pragma unroll
 	for (int q = 0; q < 8; ++q)
 	{
@@ -264,24 +214,75 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 	}
 	pc.mark(3);
 
-	// Named barriers between the row warps (0..2) and the pivot warp (3), which run one panel apart:
-	//   1  the pivot warp's inputs are in shared memory (rows arrive, pivot warp waits)
-	//   2  P is ready, as FP32 rows and as MMA operand (pivot warp arrives, rows wait)
-	//   3  the row warps among themselves (operands complete before the MMA issue)
-	constexpr int kBarInputs = 1, kBarP = 2, kBarRows = 3;
-	const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
-	if (warp == 3)
-	{
-		// ---- pivot warp: P_0 from the assembled pivot block, then P_{K+1} by look-ahead while panel K's update runs ----------
-		int pfOv = 0, pfE0 = 0, pfE1 = 0, pfSrc = 0;       // prefetch state
-		tc::nbar_sync(kBarInputs, kTcThreads);
-		invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
-		tc::fence_async_smem();
-		tc::nbar_arrive(kBarP, kTcThreads);
+	int pfOv = 0, pfE0 = 0, pfE1 = 0, pfSrc = 0;       // prefetch state of the pivot warp
 #pragma unroll 1
-		for (int K = 0; K < 5; ++K)
+	for (int K = 0; K < 6; ++K)
+	{
+		if (K > 0)
 		{
-			// staged prefetch of the next bank's inputs (lane = vertex), see TcPrefetch: one hop per panel
+			if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+			parity ^= 1u;
+			tc::fence_after_sync();
+		}
+		pc.mark(4);
+		const uint32_t colK = tb.col(16 * K);              // TMEM address of column block K (lane 0)
+		const bool inK = (t >> 4) == K;                    // this thread's row belongs to block K
+		float c[16];
+		if (warp < 3)
+		{
+			tc::tmem_ld16(colK + myLane, c);               // C[r, :], and for the rows of block K the pivot block itself
+			if (inK)
+			{
+				float4* dst = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
+#pragma unroll
+				for (int q = 0; q < 4; ++q) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+#pragma unroll
+				for (int k = 0; k < 16; ++k) c[k] = 0.0f;  // Bop[x] = 0 for the rows of block K
+			}
+		}
+		__syncthreads();
+		pc.mark(5);
+		if (warp < 3)
+		{
+			// (beside warp 3 inverting the pivot block)  Bop = C[r, :]: B operand of the update GEMM and A operand of C P
+			store_operand_row(s.op.bHi, s.op.bLo, t, c);
+			// row block K of T is REPLACED by this panel: zero it, the update GEMM then deposits P C^T there
+			if (warp == (K >> 1))
+			{
+				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb.a, 16 * K, 0));      // columns 0..63
+				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb.b, 16 * K, 0));      // columns 64..95
+				tc::tmem_wait_st();
+			}
+		}
+		if (warp == 3)
+		{
+			invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
+		}
+		tc::fence_async_smem();
+		tc::fence_before_sync();
+		__syncthreads();
+		pc.mark(6);
+		const uint32_t aH = tc::smem_addr(s.op.aHi), aL = tc::smem_addr(s.op.aLo), bH = tc::smem_addr(s.op.bHi), bL = tc::smem_addr(s.op.bLo);
+		if (t == 96)
+		{
+			// T[:, K] = C P^T (3xTF32, small terms first; the first MMA overwrites the column block)
+			tc::fence_after_sync();
+			constexpr uint32_t idP = tc::idesc_tf32(128, 16);
+			const uint32_t pH = tc::smem_addr(s.pHi), pL = tc::smem_addr(s.pLo);
+#pragma unroll
+			for (int ks = 0; ks < 2; ++ks)
+			{
+				const uint32_t off = ks * 2 * tc::kLbo;
+				tc::mma_tf32(colK, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, ks);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pL + off, tc::kLbo, tc::kSbo), idP, 1u);
+				tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, 1u);
+			}
+			tc::mma_commit(&s.bar);
+		}
+		if (warp == 3)
+		{
+			// staged prefetch of the next bank's inputs (lane = vertex), see TcPrefetch; here the pivot warp has nothing else to do
+			// until the product C P^T completes
 			const int vn = pf.bank * 32 + lane;
 			if (pf.bank >= 0 && vn < pf.nv)
 			{
@@ -305,97 +306,15 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 					for (int off = 0; off < bytes + 127; off += 128) prefetch_l2(first + (off < bytes ? off : bytes - 1));
 				}
 			}
-			tc::nbar_sync(kBarInputs, kTcThreads);           // T[K+1, K+1], (C P) and C rows of block K + 1 are in shared memory
-			invert16_lookahead(s.piv, s.lookA, s.lookC, s.P, s.pHi, s.pLo, lane);
-			tc::fence_async_smem();
-			tc::nbar_arrive(kBarP, kTcThreads);
 		}
-	}
-	else
-	{
-		// ---- row warps ---------------------------------------------------------------------------------------------------
-		float c[16];
-		tc::tmem_ld16(tb.col(0) + myLane, c);                // panel 0: C[r, :]; the rows of block 0 hold the pivot block
-		if ((t >> 4) == 0)
+		if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+		parity ^= 1u;
+		tc::fence_after_sync();
+		pc.mark(7);
+		if (warp < 3)
 		{
-			float4* dst = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
-#pragma unroll
-			for (int q = 0; q < 4; ++q) dst[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-		}
-		tc::nbar_arrive(kBarInputs, kTcThreads);
-#pragma unroll 1
-		for (int K = 0; K < 6; ++K)
-		{
-			const uint32_t colK = tb.col(16 * K);            // TMEM address of column block K (lane 0)
-			const bool inK = (t >> 4) == K;                  // this thread's row belongs to block K
-			if (K > 0)
-			{
-				if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);     // update GEMM of panel K - 1
-				parity ^= 1u;
-				tc::fence_after_sync();
-				tc::tmem_ld16(colK + myLane, c);
-			}
-			pc.mark(4);
-			if (inK)
-			{
-#pragma unroll
-				for (int k = 0; k < 16; ++k) c[k] = 0.0f;    // Bop[x] = 0 for the rows of block K
-			}
-			// Bop = C[r, :]: B operand of the update GEMM and A operand of the product C P
-			store_operand_row(s.op.bHi, s.op.bLo, t, c);
-			// row block K of T is REPLACED by this panel: zero it, the update GEMM then deposits P C^T there
-			if (warp == (K >> 1))
-			{
-				tc::tmem_zero_16lanes_x8(tc::tmem_at(tb.a, 16 * K, 0));      // columns 0..63
-				tc::tmem_zero_16lanes_x4(tc::tmem_at(tb.b, 16 * K, 0));      // columns 64..95
-				tc::tmem_wait_st();
-			}
-			tc::fence_async_smem();
-			tc::fence_before_sync();
-			tc::nbar_sync(kBarP, kTcThreads);                // P_K is there (normally long since), and so is every row's Bop
-			pc.mark(5);
-			if (t == 0)
-			{
-				// T[:, K] = C P^T (3xTF32, small terms first; the first MMA overwrites the column block)
-				tc::fence_after_sync();
-				constexpr uint32_t idP = tc::idesc_tf32(128, 16);
-				const uint32_t pH = tc::smem_addr(s.pHi), pL = tc::smem_addr(s.pLo);
-#pragma unroll
-				for (int ks = 0; ks < 2; ++ks)
-				{
-					const uint32_t off = ks * 2 * tc::kLbo;
-					tc::mma_tf32(colK, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, ks);
-					tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pL + off, tc::kLbo, tc::kSbo), idP, 1u);
-					tc::mma_tf32(colK, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), tc::smem_desc(pH + off, tc::kLbo, tc::kSbo), idP, 1u);
-				}
-				tc::mma_commit(&s.bar);
-			}
-			if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
-			parity ^= 1u;
-			tc::fence_after_sync();
-			pc.mark(6);
 			float a[16];
-			tc::tmem_ld16(colK + myLane, a);                 // (C P)[r, :]; zero for the rows of block K
-			if (K < 5)
-			{
-				// look-ahead inputs for the pivot warp: the rows of block K + 1 hand over their current pivot-block row, their
-				// (C P) row and their C row
-				float d[16];
-				if (warp == ((K + 1) >> 1)) tc::tmem_ld16(tb.col(16 * (K + 1)) + myLane, d);
-				if ((t >> 4) == K + 1)
-				{
-					float4* dp = reinterpret_cast<float4*>(s.piv + (t & 15) * kTcPs);
-					float4* ap = reinterpret_cast<float4*>(s.lookA + (t & 15) * kTcPs);
-					float4* cp = reinterpret_cast<float4*>(s.lookC + (t & 15) * kTcPs);
-#pragma unroll
-					for (int q = 0; q < 4; ++q)
-					{
-						dp[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
-						ap[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-						cp[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-					}
-				}
-			}
+			tc::tmem_ld16(colK + myLane, a);               // (C P)[r, :]; zero for the rows of block K
 			if (warp == (K >> 1))
 			{
 				// the rows of block K store -P into the pivot block (their 16 lanes cannot be written alone with this shape:
@@ -413,40 +332,38 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 				tc::tmem_st16(colK + myLane, a);
 				tc::tmem_wait_st();
 			}
-			if (K < 5) tc::nbar_arrive(kBarInputs, kTcThreads);   // (after the last read of P_K: the pivot warp overwrites it)
 			// Aop = -(C P)[r, :] for the rows outside block K, P[x, :] for the rows of block K: the negative of `a` either way
 #pragma unroll
 			for (int k = 0; k < 16; ++k) a[k] = -a[k];
 			store_operand_row(s.op.aHi, s.op.aLo, t, a);
-			tc::fence_async_smem();
-			tc::fence_before_sync();
-			tc::nbar_sync(kBarRows, 96);
-			pc.mark(7);
-			if (t == 0)
-			{
-				tc::fence_after_sync();
-				constexpr uint32_t idA = tc::idesc_tf32(128, kTcColsA), idB = tc::idesc_tf32(128, kTcColsB);
-				constexpr uint32_t rowsB = tc::operand_bytes(kTcColsA);       // B operand rows 64..95 feed matrix columns 64..95
-#pragma unroll
-				for (int ks = 0; ks < 2; ++ks)
-				{
-					const uint32_t off = ks * 2 * tc::kLbo;
-					const uint64_t dAl = tc::smem_desc(aL + off, tc::kLbo, tc::kSbo), dAh = tc::smem_desc(aH + off, tc::kLbo, tc::kSbo);
-					// small terms first: lo * hi, hi * lo, hi * hi; each as N = 64 (columns 0..63) and N = 32 (columns 64..95)
-					tc::mma_tf32(tb.a, dAl, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
-					tc::mma_tf32(tb.b, dAl, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
-					tc::mma_tf32(tb.a, dAh, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), idA, 1u);
-					tc::mma_tf32(tb.b, dAh, tc::smem_desc(bL + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
-					tc::mma_tf32(tb.a, dAh, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
-					tc::mma_tf32(tb.b, dAh, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
-				}
-				tc::mma_commit(&s.bar);
-			}
 		}
-		if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
-		parity ^= 1u;
-		tc::fence_after_sync();
+		tc::fence_async_smem();
+		tc::fence_before_sync();
+		__syncthreads();
+		if (t == 96)
+		{
+			tc::fence_after_sync();
+			constexpr uint32_t idA = tc::idesc_tf32(128, kTcColsA), idB = tc::idesc_tf32(128, kTcColsB);
+			constexpr uint32_t rowsB = tc::operand_bytes(kTcColsA);       // B operand rows 64..95 feed matrix columns 64..95
+#pragma unroll
+			for (int ks = 0; ks < 2; ++ks)
+			{
+				const uint32_t off = ks * 2 * tc::kLbo;
+				const uint64_t dAl = tc::smem_desc(aL + off, tc::kLbo, tc::kSbo), dAh = tc::smem_desc(aH + off, tc::kLbo, tc::kSbo);
+				// small terms first: lo * hi, hi * lo, hi * hi; each as N = 64 (columns 0..63) and N = 32 (columns 64..95)
+				tc::mma_tf32(tb.a, dAl, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAl, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
+				tc::mma_tf32(tb.a, dAh, tc::smem_desc(bL + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAh, tc::smem_desc(bL + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
+				tc::mma_tf32(tb.a, dAh, tc::smem_desc(bH + off, tc::kLbo, tc::kSbo), idA, 1u);
+				tc::mma_tf32(tb.b, dAh, tc::smem_desc(bH + rowsB + off, tc::kLbo, tc::kSbo), idB, 1u);
+			}
+			tc::mma_commit(&s.bar);
+		}
 	}
+	if (!tc::mbar_wait(&s.bar, parity) && t == 0) atomicExch(errFlag, 1);
+	parity ^= 1u;
+	tc::fence_after_sync();
 	pc.mark(8);
 
 	// T = -A^-1: lower triangle into the packed ("lane-slot") order

@@ -66,10 +66,6 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy writes to shared memory made visible to the async proxy (the tensor core reads its operands through it)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- named barriers (bar.sync / bar.arrive with an id and a thread count: producer / consumer hand-offs between warps) -------
-__device__ __forceinline__ void nbar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
 // ---- mbarrier -----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
