@@ -133,49 +133,6 @@ __device__ __forceinline__ void invert16_warp(const float* __restrict__ piv, flo
 	*reinterpret_cast<float4*>(l + tc::kLbo) = make_float4(lo[4], lo[5], lo[6], lo[7]);
 }
 
-// The same elimination by ALL FOUR warps of the CTA: thread t owns the two elements (row t >> 3, columns 2 (t & 7), + 1) of
-// the 16x16 block; the pivot rows, the 2x2 pivot block and a row's pivot-column entries are read from shared memory, which
-// holds the block in two copies written alternately (step q reads copy q & 1 and writes the other: one block barrier per
-// step).  One warp doing all 256 elements issues ~650 dependent instructions per panel (3 k cycles, measured); spread over
-// 128 threads a step is five LDS.64, a reciprocal and four FMAs.  buf0 = the pivot block on entry; the inverse is left in
-// `P` (FP32 rows, stride kTcPs) and in pHi / pLo (MMA operand, hi / lo halves).  Contains block barriers: all threads call it.
-__device__ __forceinline__ void invert16_block(float* __restrict__ buf0, float* __restrict__ P, float* __restrict__ pHi, float* __restrict__ pLo)
-{
-	const int t = threadIdx.x, row = t >> 3, cb = 2 * (t & 7);
-	float m0, m1;
-	{
-		const float2 v = *reinterpret_cast<const float2*>(buf0 + row * kTcPs + cb);
-		m0 = v.x; m1 = v.y;
-	}
-#pragma unroll
-	for (int q = 0; q < 8; ++q)
-	{
-		const int p = 2 * q;
-		const float* src = (q & 1) ? P : buf0;
-		float* dst = (q & 1) ? buf0 : P;
-		const float2 bt = *reinterpret_cast<const float2*>(src + p * kTcPs + p), bb = *reinterpret_cast<const float2*>(src + (p + 1) * kTcPs + p);
-		const float2 f = *reinterpret_cast<const float2*>(src + row * kTcPs + p);                // M[row][P]
-		const float2 r0 = *reinterpret_cast<const float2*>(src + p * kTcPs + cb), r1 = *reinterpret_cast<const float2*>(src + (p + 1) * kTcPs + cb);
-		const float rd = rcp_newton(__fmaf_rn(bt.x, bb.y, -__fmul_rn(bt.y, bb.x)));
-		const float i00 = __fmul_rn(bb.y, rd), i01 = -__fmul_rn(bt.y, rd), i10 = -__fmul_rn(bb.x, rd), i11 = __fmul_rn(bt.x, rd);
-		const bool isP0 = row == p, isP1 = row == p + 1, isP = isP0 || isP1;
-		const float g0 = isP0 ? -i00 : (isP1 ? -i10 : __fmaf_rn(f.x, i00, __fmul_rn(f.y, i10)));
-		const float g1 = isP0 ? -i01 : (isP1 ? -i11 : __fmaf_rn(f.x, i01, __fmul_rn(f.y, i11)));
-		m0 = __fmaf_rn(-g1, r1.x, __fmaf_rn(-g0, r0.x, isP ? 0.0f : m0));
-		m1 = __fmaf_rn(-g1, r1.y, __fmaf_rn(-g0, r0.y, isP ? 0.0f : m1));
-		if (cb == p) { m0 = -g0; m1 = -g1; }                 // the pivot columns
-		*reinterpret_cast<float2*>(dst + row * kTcPs + cb) = make_float2(m0, m1);
-		__syncthreads();
-	}
-	// eight steps: the last one wrote buf0.  P and the operand copies from the registers (nobody reads P any more).
-	*reinterpret_cast<float2*>(P + row * kTcPs + cb) = make_float2(m0, m1);
-	float h0, l0, h1, l1;
-	tc::split_tf32(m0, h0, l0);
-	tc::split_tf32(m1, h1, l1);
-	*reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pHi) + tc::operand_offset(row, cb)) = make_float2(h0, h1);
-	*reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pLo) + tc::operand_offset(row, cb)) = make_float2(l0, l1);
-}
-
 // one operand row (16 k) of thread / row `r`: hi and lo halves, four 16-byte stores each
 __device__ __forceinline__ void store_operand_row(float* __restrict__ hiBuf, float* __restrict__ loBuf, const int r, const float (&v)[16])
 {
@@ -297,7 +254,10 @@ __device__ __forceinline__ void invert_tile_tc(TcSmem& s, const TcAddr tb, uint3
 				tc::tmem_wait_st();
 			}
 		}
-		invert16_block(s.piv, s.P, s.pHi, s.pLo);         // all four warps, block barriers inside
+		if (warp == 3)
+		{
+			invert16_warp(s.piv, s.P, s.pHi, s.pLo, lane);
+		}
 		tc::fence_async_smem();
 		tc::fence_before_sync();
 		__syncthreads();
