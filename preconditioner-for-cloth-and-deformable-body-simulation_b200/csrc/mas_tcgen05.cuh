@@ -77,6 +77,7 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity)
 {
 	const uint32_t a = smem_addr(bar);
+#pragma unroll 1
 	for (uint32_t spin = 0; spin < (1u << 26); ++spin)
 	{
 		uint32_t done;

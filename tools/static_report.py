@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "preconditioner-for-cloth-and-deformable-body-simulation_b200")
-HOT = ["solve_fine_kernel", "restrict_fine_kernel", "solve_coarse_kernel", "fine_assemble_invert_kernel", "cross_bank_kernel",
+HOT = ["solve_fine_kernel", "restrict_fine_kernel", "solve_coarse_kernel", "fine_assemble_invert_tc_kernel", "coarse_invert_tc_kernel", "fine_assemble_invert_kernel", "cross_bank_kernel",
        "spmv_dot_kernel", "pull_host_kernel"]
 
 
@@ -56,6 +56,11 @@ def main():
         lines.append("  memory/sync: " + ", ".join(f"{n} x{c}" for n, c in sorted(mem.items(), key=lambda x: -x[1])))
         lines.append("  math       : " + ", ".join(f"{n} x{c}" for n, c in h.most_common(40)
                                                     if re.match(r"(FFMA|FMUL|FADD|DADD|DFMA|DMUL|MUFU|IMAD|HFMA2)", n)))
+        # Blackwell tensor-core path: tcgen05.mma = UTC*MMA, tcgen05.ld / st = LDTM / STTM, tcgen05.alloc / commit = UTCATOMSWS / UTCBAR,
+        # mbarrier = SYNCS, cvt.rna.tf32 = F2FP / I2FP-class conversions
+        tens = {n: c for n, c in h.items() if re.match(r"(UTC|LDTM|STTM|SYNCS|F2FP|FENCE|UBLKCP|UTMA)", n)}
+        if tens:
+            lines.append("  tcgen05    : " + ", ".join(f"{n} x{c}" for n, c in sorted(tens.items(), key=lambda x: -x[1])))
         lines.append("")
     out = os.path.join(ROOT, "profiles", f"{tag}_static_ptxas_sass.txt")
     open(out, "w").write("\n".join(lines) + "\n")
