@@ -123,6 +123,8 @@ public:
 		Note(mas_apply(m_handle, zDevice, residualDevice, MAS_MEM_DEVICE), "PreconditioningDevice");
 	}
 	void SetStream(void* cudaStream) { if (Ensure()) Note(mas_set_stream(m_handle, cudaStream), "SetStream"); }
+	// waits for the stream; on a sharded context also reports a peer exchange that timed out (see mas_synchronize)
+	void Synchronize() { if (Ensure()) Note(mas_synchronize(m_handle), "Synchronize"); }
 	void SetOption(int key, int value) { if (Ensure()) Note(mas_set_option(m_handle, key, value), "SetOption"); }
 	int LastStatus() const { return m_status; }
 	const char* LastError() const { return m_handle ? mas_last_error(m_handle) : "no usable sm_100 GPU (there is no CPU fallback)"; }
