@@ -9,18 +9,24 @@
 //
 // One iteration = 4 launches + the apply's own launches, captured once in a CUDA graph and replayed; the stopping test is
 // evaluated on the device (a flag turns the remaining launches of a batch into no-ops), so the host synchronises once per
-// batch of iterations, not once per iteration.
+// batch of iterations, not once per iteration.  Every kernel is launched with exactly as many CTAs as are resident at once
+// (occupancy x SM count) and strides over its rows: with one CTA per 256 rows the 1M-vertex kernels ran 1.4-2.3 waves and the
+// last, partly filled wave cost 20 % of each (profiles/r02_pcg_iteration_timeline.txt).
 //   A includes the collision Hessians of the stencils of the last PreparePreconditioner (what the preconditioner was built
 //   for, cpp:1164-1227): stiff (w (x) w) (x) (d d^T) per stencil, applied matrix-free by stencil_spmv (one thread per stencil,
 //   float atomics into Ap: with stencils the summation order, and with it the last bit of the iterates, varies from run to run).
 //   spmv_dot      Ap = A p, partial sums of p.Ap.  A is converted once per solve to a sliced-ELL layout (32-row slices,
-//                 every (block slot, entry) of a slice is 32 consecutive floats): lane = row, all loads coalesced, nine
-//                 FMAs per eleven loads and no cross-lane traffic (the CSR kernel it replaces staged blocks through
-//                 shared memory and needed a segmented shuffle scan per 32 blocks: 112 us vs 397 MB at 1M vertices)
-//   axpy_rr       alpha = rz / p.Ap;  x += alpha p;  r -= alpha Ap;  partial sums of r.r
+//                 every (block slot, entry) of a slice is 32 consecutive floats; slot 0 is the diagonal block): lane = row,
+//                 all loads coalesced, nine FMAs per eleven loads and no cross-lane traffic (the CSR kernel it replaces
+//                 staged blocks through shared memory and needed a segmented shuffle scan per 32 blocks: 112 us vs 397 MB
+//                 at 1M vertices)
+//   axpy_rr       alpha = rz / p.Ap;  r -= alpha Ap;  partial sums of r.r
 //   (apply)       z = M^-1 r
-//   dot_rz        partial sums of r.z; one thread evaluates the stopping test for this iteration
-//   update_p      beta = rz' / rz;  p = z + beta p
+//   dot_rz        partial sums of r.z
+//   update_p      x += alpha p;  beta = rz' / rz;  p = z + beta p  (p is read once for both); the last CTA evaluates the
+//                 stopping test for this iteration
+//   The vector kernels issue their first loads BEFORE they reduce the previous pass's partial sums, so the reduction's
+//   latency (dependent L2 reads, two barriers) is hidden under the memory round trip instead of preceding it.
 #include "mas_internal.h"
 
 namespace mas {
@@ -30,15 +36,14 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPcgThreads = 256;
 constexpr int kPcgWarps = kPcgThreads / 32;
-constexpr int kMaxPartials = 1024;  // CTAs per reduction pass (grid-stride beyond that)
+constexpr int kMaxPartials = 2048;  // upper bound of CTAs per reduction pass (the grids are occupancy x SM count)
 constexpr int kSpmvBatch = 4;       // block slots whose loads are in flight together in the SpMV
 constexpr int kVecUnroll = 4;       // elements per thread and trip of the vector kernels, loads in flight together
 
-// Scalars: [0] rz  [1] pAp (unused, kept in partials)  [2] rr  [3] rr0  [4] rzNew
 struct PcgState
 {
-	double rz, rr, rr0, rzNew;
-	int done, iters, it;
+	double rz, rr, rr0, alpha;   // alpha: step length of the running iteration (axpy_rr -> update_p)
+	int done, iters, it;         // done: 1 = converged, 2 = maxIter reached
 	int pad;
 };
 
@@ -63,7 +68,8 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
 }
 
 // ---- sliced-ELL copy of the caller's block CSR (once per solve) ---------------------------------------------------------
-// slice g = rows 32g .. 32g+31, width w_g = its longest row; slot (g, k, lane) holds the k-th block of row 32g+lane:
+// slice g = rows 32g .. 32g+31, width w_g = 1 + its longest row; slot (g, k, lane) holds the diagonal block of row 32g+lane
+// for k = 0 and the (k-1)-th off-diagonal block of that row after it:
 //   ellIdx[sliceStart[g] + 32 k + lane]                (column vertex, -1 = padding)
 //   ellVal[9 (sliceStart[g] + 32 k) + 32 e + lane]     (entry e of the column-major 3x3 block)
 __global__ void ell_width_kernel(const int* __restrict__ ranges, int nv, int* __restrict__ sliceSlots)
@@ -73,11 +79,12 @@ __global__ void ell_width_kernel(const int* __restrict__ ranges, int nv, int* __
 	const int row = g * 32 + lane;
 	int deg = row < nv ? ranges[row + 1] - ranges[row] : 0;
 	for (int off = 16; off > 0; off >>= 1) deg = max(deg, __shfl_xor_sync(kFull, deg, off));
-	if (lane == 0) sliceSlots[g] = 32 * deg;
+	if (lane == 0) sliceSlots[g] = 32 * (deg + 1);
 }
 
-__global__ void ell_fill_kernel(const float* __restrict__ off, const int* __restrict__ ranges, const int* __restrict__ idx, int nv,
-	const int* __restrict__ sliceStart, const int* __restrict__ sliceSlots, int* __restrict__ ellIdx, float* __restrict__ ellVal)
+__global__ void ell_fill_kernel(const float* __restrict__ diag, const float* __restrict__ off, const int* __restrict__ ranges,
+	const int* __restrict__ idx, int nv, const int* __restrict__ sliceStart, const int* __restrict__ sliceSlots, int* __restrict__ ellIdx,
+	float* __restrict__ ellVal)
 {
 	const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (g * 32 >= nv) return;
@@ -86,9 +93,9 @@ __global__ void ell_fill_kernel(const float* __restrict__ off, const int* __rest
 	const int base = sliceStart[g], width = sliceSlots[g] >> 5;
 	for (int k = 0; k < width; ++k)
 	{
-		const bool has = rs + k < re;
-		ellIdx[base + 32 * k + lane] = has ? idx[rs + k] : -1;
-		const float* m = off + 9 * (size_t)(rs + k);
+		const bool has = k == 0 ? row < nv : rs + k - 1 < re;
+		ellIdx[base + 32 * k + lane] = !has ? -1 : k == 0 ? row : idx[rs + k - 1];
+		const float* m = k == 0 ? diag + 9 * (size_t)row : off + 9 * (size_t)(rs + k - 1);
 		float* dst = ellVal + 9 * (size_t)(base + 32 * k) + lane;
 #pragma unroll
 		for (int e = 0; e < 9; ++e) dst[32 * e] = has ? m[e] : 0.0f;
@@ -114,8 +121,9 @@ __device__ __forceinline__ void reduce_partials2(const double* __restrict__ pa, 
 	for (int w = 0; w < nw; ++w) { ra += sh[w]; rb += sh[nw + w]; }  // every thread, same order
 }
 
-// Ap = A p and partial p.Ap.  One warp per 32-row slice, lane = row.
-__global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __restrict__ diag, const int* __restrict__ sliceStart,
+// Ap = A p and partial p.Ap.  One warp per 32-row slice at a time, lane = row; the warps of the (resident) grid stride over
+// the slices.
+__global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const int* __restrict__ sliceStart,
 	const int* __restrict__ sliceSlots, const int* __restrict__ ellIdx, const float* __restrict__ ellVal, const float4* __restrict__ p,
 	float4* __restrict__ Ap, int nv, double* __restrict__ partials, const volatile PcgState* st)
 {
@@ -129,15 +137,6 @@ __global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __re
 		const int row = g * 32 + lane;
 		const int base = sliceStart[g], width = sliceSlots[g] >> 5;
 		float yx = 0.f, yy = 0.f, yz = 0.f;
-		float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (row < nv)
-		{
-			const float* d = diag + 9 * (size_t)row;
-			xv = p[row];
-			yx = fmaf(d[0], xv.x, fmaf(d[3], xv.y, d[6] * xv.z));
-			yy = fmaf(d[1], xv.x, fmaf(d[4], xv.y, d[7] * xv.z));
-			yz = fmaf(d[2], xv.x, fmaf(d[5], xv.y, d[8] * xv.z));
-		}
 		// Branch-free and in batches of kSpmvBatch slots: first every load of the batch (column indices and blocks, then the
 		// gathers of p), then the FMAs.  Padding slots carry zero blocks and read p[0].  With a branch on the column index
 		// every slot cost two dependent memory round trips and the kernel ran at 3.6 TB/s.
@@ -168,6 +167,7 @@ __global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const float* __re
 		}
 		if (row < nv)
 		{
+			const float4 xv = p[row];   // the diagonal slot gathered it a moment ago
 			Ap[row] = make_float4(yx, yy, yz, 0.f);
 			dot += (double)xv.x * yx + (double)xv.y * yy + (double)xv.z * yz;
 		}
@@ -209,36 +209,49 @@ __global__ void __launch_bounds__(kPcgThreads) stencil_spmv_kernel(const Stencil
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(kPcgThreads) axpy_rr_kernel(float4* __restrict__ x, float4* __restrict__ r,
-	const float4* __restrict__ p, const float4* __restrict__ Ap, int nv, const double* __restrict__ pApPartials,
-	const double* __restrict__ pApStencilPartials, int nPartials, double* __restrict__ rrPartials, const volatile PcgState* st)
+// r -= alpha Ap, partial sums of r.r; alpha = rz / p.Ap is left in the state for update_p (x += alpha p happens there,
+// where p is read anyway)
+__global__ void __launch_bounds__(kPcgThreads) axpy_rr_kernel(float4* __restrict__ r, const float4* __restrict__ Ap, int nv,
+	const double* __restrict__ pApPartials, const double* __restrict__ pApStencilPartials, int nPartials,
+	double* __restrict__ rrPartials, PcgState* stw)
 {
 	__shared__ double sh[kPcgWarps];
+	const volatile PcgState* st = stw;
 	if (st->done) return;
+	const int stride = gridDim.x * blockDim.x;
+	int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+	float4 rv[kVecUnroll], av[kVecUnroll];
+	// all loads of the kVecUnroll elements are issued before the first use (one memory round trip, not four), and the first
+	// trip's before the reduction below
+#pragma unroll
+	for (int u = 0; u < kVecUnroll; ++u)
+	{
+		const int i = i0 + u * stride;
+		if (i < nv) { rv[u] = r[i]; av[u] = Ap[i]; }
+	}
 	double pAp = reduce_partials(pApPartials, nPartials, sh);
 	if (pApStencilPartials) pAp += reduce_partials(pApStencilPartials, nPartials, sh);
-	const float alpha = (float)(st->rz / pAp);
+	const double alphaD = st->rz / pAp;
+	const float alpha = (float)alphaD;
+	if (blockIdx.x == 0 && threadIdx.x == 0) stw->alpha = alphaD;
 	double rr = 0.0;
-	const int stride = gridDim.x * blockDim.x;
-	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += kVecUnroll * stride)
+	while (i0 < nv)
 	{
-		// all loads of the kVecUnroll elements are issued before the first use (one memory round trip, not four)
-		float4 xv[kVecUnroll], rv[kVecUnroll], pv[kVecUnroll], av[kVecUnroll];
-#pragma unroll
-		for (int u = 0; u < kVecUnroll; ++u)
-		{
-			const int i = i0 + u * stride;
-			if (i < nv) { xv[u] = x[i]; rv[u] = r[i]; pv[u] = p[i]; av[u] = Ap[i]; }
-		}
 #pragma unroll
 		for (int u = 0; u < kVecUnroll; ++u)
 		{
 			const int i = i0 + u * stride;
 			if (i >= nv) break;
-			xv[u].x = fmaf(alpha, pv[u].x, xv[u].x); xv[u].y = fmaf(alpha, pv[u].y, xv[u].y); xv[u].z = fmaf(alpha, pv[u].z, xv[u].z);
 			rv[u].x = fmaf(-alpha, av[u].x, rv[u].x); rv[u].y = fmaf(-alpha, av[u].y, rv[u].y); rv[u].z = fmaf(-alpha, av[u].z, rv[u].z);
-			x[i] = xv[u]; r[i] = rv[u];
+			r[i] = rv[u];
 			rr += (double)rv[u].x * rv[u].x + (double)rv[u].y * rv[u].y + (double)rv[u].z * rv[u].z;
+		}
+		i0 += kVecUnroll * stride;
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i < nv) { rv[u] = r[i]; av[u] = Ap[i]; }
 		}
 	}
 	const double t = block_sum(rr, sh);
@@ -274,37 +287,52 @@ __global__ void __launch_bounds__(kPcgThreads) dot_kernel(const float4* __restri
 }
 
 // mode 0 (setup): rr0 = rr = sum(rrPartials), rz = sum(rzPartials), p = z, it = 0
-// mode 1 (iteration): beta = rz'/rz, p = z + beta p; block 0 records rr, the stopping test and the iteration count.
-// The flag written here is read only by LATER launches, so all CTAs of one launch see the same value.
-__global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restrict__ p, const float4* __restrict__ z, int nv,
-	const double* __restrict__ rzPartials, const double* __restrict__ rrPartials, int nPartials, double tol2, int mode,
-	PcgState* stw)
+// mode 1 (iteration): x += alpha p, beta = rz'/rz, p = z + beta p; the last CTA records rr, the stopping test and the
+// iteration count.  The flag written here is read only by LATER launches, so all CTAs of one launch see the same value.
+__global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restrict__ x, float4* __restrict__ p, const float4* __restrict__ z,
+	int nv, const double* __restrict__ rzPartials, const double* __restrict__ rrPartials, int nPartials, double tol2, int maxIter,
+	int mode, PcgState* stw)
 {
 	__shared__ double sh[2 * kPcgWarps];
 	volatile PcgState* st = stw;
 	if (st->done) return;
+	const int stride = gridDim.x * blockDim.x;
+	int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+	float4 zv[kVecUnroll], pv[kVecUnroll], xv[kVecUnroll];
+	const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+	for (int u = 0; u < kVecUnroll; ++u)   // first trip's loads before the reduction
+	{
+		const int i = i0 + u * stride;
+		if (i < nv) { zv[u] = z[i]; pv[u] = mode == 0 ? zero : p[i]; xv[u] = mode == 0 ? zero : x[i]; }
+	}
 	double rzNew, rr;
 	reduce_partials2(rzPartials, rrPartials, nPartials, sh, rzNew, rr);
 	const double rzOld = st->rz;
 	const float beta = mode == 0 ? 0.f : (float)(rzNew / rzOld);
-	const int stride = gridDim.x * blockDim.x;
-	for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nv; i0 += kVecUnroll * stride)
+	const float alpha = mode == 0 ? 0.f : (float)st->alpha;
+	while (i0 < nv)
 	{
-		float4 zv[kVecUnroll], pv[kVecUnroll];
-#pragma unroll
-		for (int u = 0; u < kVecUnroll; ++u)
-		{
-			const int i = i0 + u * stride;
-			if (i < nv) { zv[u] = z[i]; pv[u] = mode == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : p[i]; }
-		}
 #pragma unroll
 		for (int u = 0; u < kVecUnroll; ++u)
 		{
 			const int i = i0 + u * stride;
 			if (i >= nv) break;
+			if (mode != 0)
+			{
+				xv[u].x = fmaf(alpha, pv[u].x, xv[u].x); xv[u].y = fmaf(alpha, pv[u].y, xv[u].y); xv[u].z = fmaf(alpha, pv[u].z, xv[u].z);
+				x[i] = xv[u];
+			}
 			pv[u].x = fmaf(beta, pv[u].x, zv[u].x); pv[u].y = fmaf(beta, pv[u].y, zv[u].y); pv[u].z = fmaf(beta, pv[u].z, zv[u].z);
 			pv[u].w = 0.f;
 			p[i] = pv[u];
+		}
+		i0 += kVecUnroll * stride;
+#pragma unroll
+		for (int u = 0; u < kVecUnroll; ++u)
+		{
+			const int i = i0 + u * stride;
+			if (i < nv) { zv[u] = z[i]; pv[u] = mode == 0 ? zero : p[i]; xv[u] = mode == 0 ? zero : x[i]; }
 		}
 	}
 	// grid-wide agreement: the state is rewritten by the LAST CTA to finish reading it
@@ -323,6 +351,7 @@ __global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restric
 			st->it += 1;
 			st->iters = st->it;
 			if (rr < tol2 * st->rr0) st->done = 1;
+			else if (st->it >= maxIter) st->done = 2;
 		}
 		__threadfence();
 	}
@@ -362,12 +391,24 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	PcgState* state = reinterpret_cast<PcgState*>(c->pcgState.p);
 	float4 *r = c->pcgR.p, *z = usePrecond ? c->pcgZ.p : c->pcgR.p, *p = c->pcgP.p, *Ap = c->pcgAp.p;
 
-	int grid = cdiv(nv, kPcgThreads);
-	if (grid > kMaxPartials) grid = kMaxPartials;
-	int gridSpmv = cdiv(cdiv(nv, 32), kPcgWarps);
-	if (gridSpmv > kMaxPartials) gridSpmv = kMaxPartials;
-	// all three partial arrays are summed over `nPart` entries: zero them once, passes fill what they use
-	const int nPart = grid > gridSpmv ? grid : gridSpmv;
+	// resident grids: occupancy x SM count, never more CTAs than there is work for
+	auto resident = [&](const void* kernel, long long workCtas) -> int {
+		int perSm = 1;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kPcgThreads, 0) != cudaSuccess || perSm < 1) perSm = 1;
+		long long g = (long long)perSm * c->smCount;
+		if (g > workCtas) g = workCtas;
+		if (g > kMaxPartials) g = kMaxPartials;
+		return g < 1 ? 1 : (int)g;
+	};
+	const long long vecCtas = cdiv(nv, kPcgThreads);
+	const int gridAxpy = resident((const void*)axpy_rr_kernel, vecCtas);
+	const int gridDot = resident((const void*)dot_kernel, vecCtas);
+	const int gridUpdate = resident((const void*)update_p_kernel, vecCtas);
+	const int gridSpmv = resident((const void*)spmv_dot_kernel, cdiv(cdiv(nv, 32), kPcgWarps));
+	// every partial array is summed over `nPart` entries: zeroed once, and each array is always filled by the same grid
+	// (p.Ap: gridSpmv, r.r: gridAxpy, r.z: gridDot, collision part of p.Ap: gridStencil), so no stale entry survives a pass
+	int nPart = gridAxpy;
+	for (int g : { gridDot, gridUpdate, gridSpmv, gridStencil }) nPart = g > nPart ? g : nPart;
 	const double tol2 = (double)relTol * (double)relTol;
 
 	// sliced-ELL copy of A (see ell_fill_kernel): two small passes, a scan and one pass over the blocks
@@ -382,7 +423,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	MAS_CUDA(c, cudaStreamSynchronize(st));
 	if (int rc = reserve(c, c->pcgEllIdx, (size_t)(totalSlots > 0 ? totalSlots : 1))) return rc;
 	if (int rc = reserve(c, c->pcgEllVal, (size_t)(totalSlots > 0 ? totalSlots : 1) * 9)) return rc;
-	ell_fill_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(off, ranges, idx, nv, c->pcgSliceStart.p, c->pcgSliceSlots.p,
+	ell_fill_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(diag, off, ranges, idx, nv, c->pcgSliceStart.p, c->pcgSliceSlots.p,
 		c->pcgEllIdx.p, c->pcgEllVal.p);
 
 	MAS_CUDA(c, cudaMemsetAsync(state, 0, sizeof(PcgState), st));
@@ -394,9 +435,9 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		return apply_end(c, r, z);
 	};
 	if (int rc = precondition()) return rc;
-	dot_kernel<<<grid, kPcgThreads, 0, st>>>(r, r, nv, pRR, state);
-	dot_kernel<<<grid, kPcgThreads, 0, st>>>(r, z, nv, pRZ, state);
-	update_p_kernel<<<grid, kPcgThreads, 0, st>>>(p, z, nv, pRZ, pRR, nPart, tol2, 0, state);
+	dot_kernel<<<gridAxpy, kPcgThreads, 0, st>>>(r, r, nv, pRR, state);   // pRR always holds gridAxpy partials (axpy_rr refills it)
+	dot_kernel<<<gridDot, kPcgThreads, 0, st>>>(r, z, nv, pRZ, state);
+	update_p_kernel<<<gridUpdate, kPcgThreads, 0, st>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 0, state);
 	MAS_CUDA(c, cudaGetLastError());
 
 	// one iteration, captured once
@@ -411,21 +452,23 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
 	if (rc == MAS_OK)
 	{
-		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(diag, c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
+		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
 			nv, pA, state);
 		if (nStencil > 0)
 			stencil_spmv_kernel<<<gridStencil, kPcgThreads, 0, cap>>>(c->stencils.p, nStencil, p, Ap, pS, state);
-		axpy_rr_kernel<<<grid, kPcgThreads, 0, cap>>>(x, r, p, Ap, nv, pA, nStencil > 0 ? pS : nullptr, nPart, pRR, state);
+		axpy_rr_kernel<<<gridAxpy, kPcgThreads, 0, cap>>>(r, Ap, nv, pA, nStencil > 0 ? pS : nullptr, nPart, pRR, state);
 		c->applyLaunches = 0;
 		if (usePrecond) rc = apply_forked(c, r, z, cap);   // coarse chain concurrent with the head of the fine solve
-		dot_kernel<<<grid, kPcgThreads, 0, cap>>>(r, z, nv, pRZ, state);
-		update_p_kernel<<<grid, kPcgThreads, 0, cap>>>(p, z, nv, pRZ, pRR, nPart, tol2, 1, state);
+		dot_kernel<<<gridDot, kPcgThreads, 0, cap>>>(r, z, nv, pRZ, state);
+		update_p_kernel<<<gridUpdate, kPcgThreads, 0, cap>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 1, state);
 	}
 	c->pcgLaunchesPerIter = 4 + (nStencil > 0 ? 1 : 0) + (usePrecond ? c->applyLaunches : 0);
 	c->applyLaunches = savedLaunches;
 	cudaError_t e = cudaStreamEndCapture(cap, &graph);
 	c->stream = saved;
 	if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;
+	// same launch priorities as the apply's own graph: the coarse chain ahead of the streaming kernels it runs beside
+	if (rc == MAS_OK && usePrecond) rc = prioritize_apply_graph(c, graph);
 	if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
 	if (graph) cudaGraphDestroy(graph);
 	cudaStreamDestroy(cap);
@@ -452,7 +495,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	cudaGraphExecDestroy(exec);
 	if (itersOut) *itersOut = host.iters;
 	if (relResOut) *relResOut = host.rr0 > 0.0 ? (float)sqrt(host.rr / host.rr0) : 0.f;
-	c->pcgConverged = host.done;
+	c->pcgConverged = host.done == 1;
 	return MAS_OK;
 }
 

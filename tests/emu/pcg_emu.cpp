@@ -40,10 +40,12 @@ int main()
 	double* pRZ = pRR + kMaxPartials;
 	PcgState state = {};
 	float4* z = r.data();                                   // usePrecond = 0
-	int grid = cdiv(nv, kPcgThreads);
-	if (grid > kMaxPartials) grid = kMaxPartials;
-	int gridSpmv = cdiv(cdiv(nv, 32), kPcgWarps);
-	if (gridSpmv > kMaxPartials) gridSpmv = kMaxPartials;
+	// fewer CTAs than rows / 256 (as the occupancy-sized launches of pcg_solve have on large meshes): the kernels' strided
+	// trips, the reloads inside them and the ragged last trip are all exercised
+	int grid = cdiv(cdiv(nv, kPcgThreads), 3);
+	if (grid < 1) grid = 1;
+	int gridSpmv = cdiv(cdiv(cdiv(nv, 32), kPcgWarps), 3);
+	if (gridSpmv < 1) gridSpmv = 1;
 	const int nPart = grid > gridSpmv ? grid : gridSpmv;
 	const double tol2 = (double)relTol * (double)relTol;
 
@@ -55,21 +57,21 @@ int main()
 	std::vector<int> ellIdx((size_t)(totalSlots > 0 ? totalSlots : 1));
 	std::vector<float> ellVal((size_t)(totalSlots > 0 ? totalSlots : 1) * 9);
 	emu::launch(cdiv((long long)nSlices * 32, 256), 256, [&] {
-		ell_fill_kernel(off.data(), ranges.data(), idx.data(), nv, sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data());
+		ell_fill_kernel(diag.data(), off.data(), ranges.data(), idx.data(), nv, sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data());
 	});
 
 	emu::launch(cdiv(nv, 256), 256, [&] { copy_b_kernel(b.data(), r.data(), x.data(), nv); });
 	emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), r.data(), nv, pRR, &state); });
 	emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
-	emu::launch(grid, kPcgThreads, [&] { update_p_kernel(p.data(), z, nv, pRZ, pRR, nPart, tol2, 0, &state); });
+	emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 0, &state); });
 	for (int it = 0; it < iterations; ++it)
 	{
 		emu::launch(gridSpmv, kPcgThreads, [&] {
-			spmv_dot_kernel(diag.data(), sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data(), p.data(), Ap.data(), nv, pA, &state);
+			spmv_dot_kernel(sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data(), p.data(), Ap.data(), nv, pA, &state);
 		});
-		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(x.data(), r.data(), p.data(), Ap.data(), nv, pA, nullptr, nPart, pRR, &state); });
+		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(r.data(), Ap.data(), nv, pA, nullptr, nPart, pRR, &state); });
 		emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
-		emu::launch(grid, kPcgThreads, [&] { update_p_kernel(p.data(), z, nv, pRZ, pRR, nPart, tol2, 1, &state); });
+		emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 1, &state); });
 	}
 	fwrite(x.data(), 16, (size_t)nv, stdout);
 	fwrite(r.data(), 16, (size_t)nv, stdout);
