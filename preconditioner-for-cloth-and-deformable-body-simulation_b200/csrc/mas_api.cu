@@ -197,7 +197,7 @@ static void free_all(Context* c)
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
 	release(c->pcgR); release(c->pcgZ); release(c->pcgP); release(c->pcgAp); release(c->pcgB); release(c->pcgX);
 	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);
-	release(c->pcgSliceSlots); release(c->pcgSliceStart); release(c->pcgEllVal);
+	release(c->pcgSliceSlots); release(c->pcgSliceStart); release(c->pcgEllIdx); release(c->pcgEllVal);
 }
 
 }  // namespace mas

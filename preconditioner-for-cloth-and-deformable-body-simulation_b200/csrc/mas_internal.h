@@ -173,7 +173,7 @@ struct Context
 	DevBuf<unsigned char> pcgState;
 	DevBuf<float> pcgDiag, pcgOff;
 	DevBuf<int> pcgRanges, pcgIdx;
-	DevBuf<int> pcgSliceSlots, pcgSliceStart;   // sliced-ELL copy of A built by every mas_pcg_solve (mas_pcg.cu: ell_fill_kernel)
+	DevBuf<int> pcgSliceSlots, pcgSliceStart, pcgEllIdx;   // sliced-ELL copy of A built by every mas_pcg_solve
 	DevBuf<float> pcgEllVal;
 	int pcgLaunchesPerIter = 0;
 	int pcgConverged = 0;

@@ -37,30 +37,14 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kPcgThreads = 256;
 constexpr int kPcgWarps = kPcgThreads / 32;
 constexpr int kMaxPartials = 2048;  // upper bound of CTAs per reduction pass (the grids are occupancy x SM count)
-// SpMV staging (spmv_dot_kernel): every warp streams its part of the ELL image through its own ring of shared-memory
-// buffers, filled by bulk asynchronous copies (TMA) that complete on an mbarrier
-constexpr int kSpmvThreads = 512;
-constexpr int kSpmvWarps = kSpmvThreads / 32;
-constexpr int kSlotWords = 320;      // one block slot of a slice: 9 x 32 values + 32 column indices
-constexpr int kChunkSlots = 3;       // slots per bulk copy (3,840 bytes)
-constexpr int kSpmvStages = 3;       // buffers per warp: two copies in flight while the third is consumed
-constexpr int kChunkWords = kChunkSlots * kSlotWords;
-constexpr int kGatherAhead = 3;      // chunks between the gathers of p and their use
-constexpr int kQRing = kGatherAhead + 1;
-constexpr int kIdxRing = 2;          // chunks between the loads of the column indices and the gathers that use them
-constexpr int kIdxAhead = kGatherAhead + kIdxRing;
-constexpr int kSpmvUnroll = 4;       // a common multiple of both ring lengths
-constexpr int kSpmvPrologue = 8;     // steps before chunk 0 (>= kIdxAhead, a multiple of kSpmvUnroll)
-static_assert(kSpmvUnroll % kQRing == 0 && kSpmvUnroll % kIdxRing == 0 && kSpmvPrologue % kSpmvUnroll == 0 && kSpmvPrologue >= kIdxAhead, "");
-constexpr size_t kSpmvSmemBytes = (size_t)kSpmvWarps * kSpmvStages * kChunkWords * sizeof(float);
+constexpr int kSpmvBatch = 4;       // block slots whose loads are in flight together in the SpMV
 constexpr int kVecUnroll = 4;       // elements per thread and trip of the vector kernels, loads in flight together
 
 struct PcgState
 {
 	double rz, rr, rr0, alpha;   // alpha: step length of the running iteration (axpy_rr -> update_p)
 	int done, iters, it;         // done: 1 = converged, 2 = maxIter reached
-	int pad;                     // update_p's ticket counter
-	int stageErr, pad2;          // spmv_dot: a bulk copy never completed
+	int pad;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh)
@@ -84,37 +68,37 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
 }
 
 // ---- sliced-ELL copy of the caller's block CSR (once per solve) ---------------------------------------------------------
-// slice g = rows 32g .. 32g+31, width w_g = 1 + its longest row (in slots); slot k of slice g is one 1,280-byte record
-//   ell[kSlotWords (sliceStart[g] + k) + 32 e + lane]   e = 0..8: entry e of the column-major 3x3 block of row 32g+lane
-//                                                      e = 9   : its column vertex (int bits; -1 = padding, zero block)
-// k = 0 is the row's diagonal block, k >= 1 its (k-1)-th off-diagonal block.  The slices follow each other without gaps, so
-// any range of slots - across slice boundaries too - is one contiguous, 16-byte aligned piece of memory.
-__global__ void ell_width_kernel(const int* __restrict__ ranges, int nv, int nSlices, int* __restrict__ sliceSlots)
+// slice g = rows 32g .. 32g+31, width w_g = 1 + its longest row; slot (g, k, lane) holds the diagonal block of row 32g+lane
+// for k = 0 and the (k-1)-th off-diagonal block of that row after it:
+//   ellIdx[sliceStart[g] + 32 k + lane]                (column vertex, -1 = padding)
+//   ellVal[9 (sliceStart[g] + 32 k) + 32 e + lane]     (entry e of the column-major 3x3 block)
+__global__ void ell_width_kernel(const int* __restrict__ ranges, int nv, int* __restrict__ sliceSlots)
 {
 	const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (g > nSlices) return;
+	if (g * 32 >= nv) return;
 	const int row = g * 32 + lane;
 	int deg = row < nv ? ranges[row + 1] - ranges[row] : 0;
 	for (int off = 16; off > 0; off >>= 1) deg = max(deg, __shfl_xor_sync(kFull, deg, off));
-	if (lane == 0) sliceSlots[g] = g < nSlices ? deg + 1 : 0;   // entry nSlices: the scan leaves the total there
+	if (lane == 0) sliceSlots[g] = 32 * (deg + 1);
 }
 
 __global__ void ell_fill_kernel(const float* __restrict__ diag, const float* __restrict__ off, const int* __restrict__ ranges,
-	const int* __restrict__ idx, int nv, const int* __restrict__ sliceStart, float* __restrict__ ell)
+	const int* __restrict__ idx, int nv, const int* __restrict__ sliceStart, const int* __restrict__ sliceSlots, int* __restrict__ ellIdx,
+	float* __restrict__ ellVal)
 {
 	const int lane = threadIdx.x & 31, g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (g * 32 >= nv) return;
 	const int row = g * 32 + lane;
 	const int rs = row < nv ? ranges[row] : 0, re = row < nv ? ranges[row + 1] : 0;
-	const int base = sliceStart[g], width = sliceStart[g + 1] - base;
+	const int base = sliceStart[g], width = sliceSlots[g] >> 5;
 	for (int k = 0; k < width; ++k)
 	{
 		const bool has = k == 0 ? row < nv : rs + k - 1 < re;
+		ellIdx[base + 32 * k + lane] = !has ? -1 : k == 0 ? row : idx[rs + k - 1];
 		const float* m = k == 0 ? diag + 9 * (size_t)row : off + 9 * (size_t)(rs + k - 1);
-		float* dst = ell + (size_t)kSlotWords * (base + k) + lane;
+		float* dst = ellVal + 9 * (size_t)(base + 32 * k) + lane;
 #pragma unroll
 		for (int e = 0; e < 9; ++e) dst[32 * e] = has ? m[e] : 0.0f;
-		dst[32 * 9] = __int_as_float(!has ? -1 : k == 0 ? row : idx[rs + k - 1]);
 	}
 }
 
@@ -137,175 +121,56 @@ __device__ __forceinline__ void reduce_partials2(const double* __restrict__ pa, 
 	for (int w = 0; w < nw; ++w) { ra += sh[w]; rb += sh[nw + w]; }  // every thread, same order
 }
 
-// ---- bulk asynchronous copies global -> shared (TMA, cp.async.bulk) completing on an mbarrier ----------------------------
-#ifdef MAS_CPU_EMULATION
-__device__ __forceinline__ void stage_init(unsigned long long*) {}
-__device__ __forceinline__ void stage_copy(float* dst, const float* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ bool stage_wait(unsigned long long*, unsigned) { return true; }
-#else
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void stage_init(unsigned long long* bar)
+// Ap = A p and partial p.Ap.  One warp per 32-row slice at a time, lane = row; the warps of the (resident) grid stride over
+// the slices.
+__global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const int* __restrict__ sliceStart,
+	const int* __restrict__ sliceSlots, const int* __restrict__ ellIdx, const float* __restrict__ ellVal, const float4* __restrict__ p,
+	float4* __restrict__ Ap, int nv, double* __restrict__ partials, const volatile PcgState* st)
 {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
-}
-// one thread: expect `bytes` on the barrier, then start the copy (src, dst and bytes are multiples of 16)
-__device__ __forceinline__ void stage_copy(float* dst, const float* src, unsigned bytes, unsigned long long* bar)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-		"r"(bytes), "r"(smem_u32(bar))
-		: "memory");
-}
-// bounded: a protocol bug must not hang the GPU
-__device__ __forceinline__ bool stage_wait(unsigned long long* bar, unsigned parity)
-{
-	const unsigned a = smem_u32(bar);
-#pragma unroll 1
-	for (unsigned spin = 0; spin < (1u << 26); ++spin)
-	{
-		unsigned done;
-		asm volatile(
-			"{\n\t"
-			".reg .pred p;\n\t"
-			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			"selp.u32 %0, 1, 0, p;\n\t"
-			"}\n"
-			: "=r"(done)
-			: "r"(a), "r"(parity)
-			: "memory");
-		if (done) return true;
-	}
-	return false;
-}
-#endif
-
-#ifdef MAS_CPU_EMULATION
-#define MAS_PCG_DYNAMIC_SMEM(name) unsigned char* name = emu_dynamic_smem()
-#else
-#define MAS_PCG_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
-#endif
-
-// Ap = A p and partial p.Ap.  The slices are dealt to the warps of the grid in contiguous runs; a warp's run is one contiguous
-// stretch of the ELL image, which it pulls through its ring of kSpmvStages shared-memory buffers in chunks of kChunkSlots
-// slots: lane 0 issues the bulk copies (two chunks ahead), all lanes wait on the chunk's mbarrier and read their own column
-// of it (lane = row, conflict-free).  Nothing of A lands in registers before it is used, so the bytes in flight per SM are
-// bounded by shared memory (2/3 of 180 KB), not by the register file: the register-staged kernel this replaces (40 loads per
-// warp and batch, then the dependent gathers of p) held 5.4 TB/s at 50 % occupancy, stalled on the scoreboard and on the
-// load/store queue (profiles/r02_spmv_register_staged_ncu.txt).
-// Slice boundaries may fall inside a chunk.
-__global__ void __launch_bounds__(kSpmvThreads, 1) spmv_dot_kernel(const int* __restrict__ sliceStart, const float* __restrict__ ell,
-	const float4* __restrict__ p, float4* __restrict__ Ap, int nv, double* __restrict__ partials, const volatile PcgState* st,
-	int* __restrict__ err)
-{
-	MAS_PCG_DYNAMIC_SMEM(smem);
-	__shared__ unsigned long long bars[kSpmvWarps * kSpmvStages];
-	__shared__ double sh[kSpmvWarps];
+	__shared__ double sh[kPcgWarps];
 	if (st->done) return;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nSlices = (nv + 31) >> 5;
-	const long long nWarps = (long long)gridDim.x * kSpmvWarps, wg = (long long)blockIdx.x * kSpmvWarps + warp;
-	const int s0 = (int)(nSlices * wg / nWarps), s1 = (int)(nSlices * (wg + 1) / nWarps);
-	float* ring = reinterpret_cast<float*>(smem) + (size_t)warp * kSpmvStages * kChunkWords;
-	unsigned long long* bar = bars + warp * kSpmvStages;
-	if (lane == 0)
-		for (int i = 0; i < kSpmvStages; ++i) stage_init(bar + i);
-#ifndef MAS_CPU_EMULATION
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-	__syncwarp();
-
 	double dot = 0.0;
-	if (s1 > s0)
+	for (int g = blockIdx.x * kPcgWarps + warp; g < nSlices; g += gridDim.x * kPcgWarps)
 	{
-		const int slot0 = sliceStart[s0], nSlots = sliceStart[s1] - slot0;
-		const int nChunks = (nSlots + kChunkSlots - 1) / kChunkSlots;
-		const float* src = ell + (size_t)kSlotWords * slot0;
-		auto issue = [&](int c) {   // lane 0
-			const int n = nSlots - c * kChunkSlots < kChunkSlots ? nSlots - c * kChunkSlots : kChunkSlots;
-			stage_copy(ring + (c % kSpmvStages) * kChunkWords, src + (size_t)c * kChunkWords, (unsigned)(n * kSlotWords * sizeof(float)),
-				bar + c % kSpmvStages);
-		};
-		if (lane == 0)
-			for (int c = 0; c < kSpmvStages && c < nChunks; ++c) issue(c);
-		// widths of the run's slices, 32 at a time in the lanes
-		int slice = s0, metaBase = s0;
-		int meta = s0 + lane < s1 ? sliceStart[s0 + lane + 1] - sliceStart[s0 + lane] : 0;
-		int width = __shfl_sync(kFull, meta, 0), kIn = 0;
+		const int row = g * 32 + lane;
+		const int base = sliceStart[g], width = sliceSlots[g] >> 5;
 		float yx = 0.f, yy = 0.f, yz = 0.f;
-		float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-		bool ok = true;
-		// Three software pipelines per warp, all in units of chunks: bulk copies (kSpmvStages - 1 ahead, into shared memory),
-		// column indices (kIdxAhead ahead, plain loads of the same records' index words) and the gathers of p
-		// (kGatherAhead ahead, into a register ring).  Chunk c is multiplied when its copy has landed and its gathers, issued
-		// three steps earlier, have returned: no step waits on a load issued in the same step.  (With the gathers only one
-		// chunk ahead the per-chunk step took one L2 round trip under load, ~1 us, and the kernel was latency-bound at 82 us.)
-		int ci[kIdxRing][kChunkSlots];
-		float4 q[kQRing][kChunkSlots];
-		for (int c0 = -kSpmvPrologue; c0 < nChunks; c0 += kSpmvUnroll)
+		// Branch-free and in batches of kSpmvBatch slots: first every load of the batch (column indices and blocks, then the
+		// gathers of p), then the FMAs.  Padding slots carry zero blocks and read p[0].  With a branch on the column index
+		// every slot cost two dependent memory round trips and the kernel ran at 3.6 TB/s.
+		for (int k0 = 0; k0 < width; k0 += kSpmvBatch)
 		{
+			int c[kSpmvBatch];
+			float v[kSpmvBatch][9];
+			float4 q[kSpmvBatch];
 #pragma unroll
-			for (int j = 0; j < kSpmvUnroll; ++j)
+			for (int u = 0; u < kSpmvBatch; ++u)
 			{
-				const int c = c0 + j;   // c mod kSpmvUnroll == j: every ring index below is a compile-time constant
-				const int cg = c + kGatherAhead, cx = c + kIdxAhead;
-				if (cg >= 0 && cg < nChunks)
-				{
+				const bool in = k0 + u < width;
+				const int slot = base + 32 * (in ? k0 + u : k0);
+				c[u] = in ? ellIdx[slot + lane] : -1;
+				const float* m = ellVal + 9 * (size_t)slot + lane;
 #pragma unroll
-					for (int u = 0; u < kChunkSlots; ++u)
-					{
-						const int col = ci[(j + kGatherAhead) % kIdxRing][u];
-						q[(j + kGatherAhead) % kQRing][u] = p[col < 0 ? 0 : col];
-					}
-				}
-				if (cx >= 0 && cx < nChunks)
-				{
+				for (int e = 0; e < 9; ++e) v[u][e] = in ? m[32 * e] : 0.0f;
+			}
 #pragma unroll
-					for (int u = 0; u < kChunkSlots; ++u)
-					{
-						const int slot = cx * kChunkSlots + u;
-						ci[(j + kIdxAhead) % kIdxRing][u] = slot < nSlots ? __float_as_int(src[(size_t)slot * kSlotWords + 9 * 32 + lane]) : -1;
-					}
-				}
-				if (c < 0 || c >= nChunks) continue;
-				ok = stage_wait(bar + c % kSpmvStages, (unsigned)(c / kSpmvStages) & 1u) && ok;
-				__syncwarp();
-				const float* buf = ring + (c % kSpmvStages) * kChunkWords;
-				const int n = nSlots - c * kChunkSlots;
+			for (int u = 0; u < kSpmvBatch; ++u) q[u] = p[c[u] < 0 ? 0 : c[u]];
 #pragma unroll
-				for (int u = 0; u < kChunkSlots; ++u)
-				{
-					if (u >= n) break;
-					const float* m = buf + u * kSlotWords + lane;
-					const float4 pv = q[j % kQRing][u];
-					if (kIn == 0) xv = pv;                       // slot 0 is the diagonal block: its column is the row itself
-					yx = fmaf(m[0], pv.x, fmaf(m[96], pv.y, fmaf(m[192], pv.z, yx)));
-					yy = fmaf(m[32], pv.x, fmaf(m[128], pv.y, fmaf(m[224], pv.z, yy)));
-					yz = fmaf(m[64], pv.x, fmaf(m[160], pv.y, fmaf(m[256], pv.z, yz)));
-					if (++kIn == width)
-					{
-						const int row = slice * 32 + lane;
-						if (row < nv)
-						{
-							Ap[row] = make_float4(yx, yy, yz, 0.f);
-							dot += (double)xv.x * yx + (double)xv.y * yy + (double)xv.z * yz;
-						}
-						yx = yy = yz = 0.f;
-						kIn = 0;
-						++slice;
-						if (slice - metaBase == 32 && slice < s1)
-						{
-							metaBase = slice;
-							meta = slice + lane < s1 ? sliceStart[slice + lane + 1] - sliceStart[slice + lane] : 0;
-						}
-						width = __shfl_sync(kFull, meta, (slice - metaBase) & 31);
-					}
-				}
-				// the buffer is free: every lane has read its column of chunk c
-				__syncwarp();
-				if (lane == 0 && c + kSpmvStages < nChunks) issue(c + kSpmvStages);
+			for (int u = 0; u < kSpmvBatch; ++u)
+			{
+				yx = fmaf(v[u][0], q[u].x, fmaf(v[u][3], q[u].y, fmaf(v[u][6], q[u].z, yx)));
+				yy = fmaf(v[u][1], q[u].x, fmaf(v[u][4], q[u].y, fmaf(v[u][7], q[u].z, yy)));
+				yz = fmaf(v[u][2], q[u].x, fmaf(v[u][5], q[u].y, fmaf(v[u][8], q[u].z, yz)));
 			}
 		}
-		if (!ok && lane == 0) *err = 1;
+		if (row < nv)
+		{
+			const float4 xv = p[row];   // the diagonal slot gathered it a moment ago
+			Ap[row] = make_float4(yx, yy, yz, 0.f);
+			dot += (double)xv.x * yx + (double)xv.y * yy + (double)xv.z * yz;
+		}
 	}
 	const double t = block_sum(dot, sh);
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
@@ -539,27 +404,27 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	const int gridAxpy = resident((const void*)axpy_rr_kernel, vecCtas);
 	const int gridDot = resident((const void*)dot_kernel, vecCtas);
 	const int gridUpdate = resident((const void*)update_p_kernel, vecCtas);
-	int gridSpmv = cdiv(cdiv(nv, 32), kSpmvWarps);          // one CTA per SM: its buffers take 180 KB of shared memory
-	if (gridSpmv > c->smCount) gridSpmv = c->smCount;
-	MAS_CUDA(c, cudaFuncSetAttribute((const void*)spmv_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpmvSmemBytes));
+	const int gridSpmv = resident((const void*)spmv_dot_kernel, cdiv(cdiv(nv, 32), kPcgWarps));
 	// every partial array is summed over `nPart` entries: zeroed once, and each array is always filled by the same grid
 	// (p.Ap: gridSpmv, r.r: gridAxpy, r.z: gridDot, collision part of p.Ap: gridStencil), so no stale entry survives a pass
 	int nPart = gridAxpy;
 	for (int g : { gridDot, gridUpdate, gridSpmv, gridStencil }) nPart = g > nPart ? g : nPart;
 	const double tol2 = (double)relTol * (double)relTol;
 
-	// sliced-ELL copy of A (see ell_fill_kernel): widths, a scan (its last entry is the total) and one pass over the blocks
+	// sliced-ELL copy of A (see ell_fill_kernel): two small passes, a scan and one pass over the blocks
 	const int nSlices = cdiv(nv, 32);
-	if (int rc = reserve(c, c->pcgSliceSlots, (size_t)nSlices + 1)) return rc;
-	if (int rc = reserve(c, c->pcgSliceStart, (size_t)nSlices + 1)) return rc;
+	if (int rc = reserve(c, c->pcgSliceSlots, (size_t)nSlices)) return rc;
+	if (int rc = reserve(c, c->pcgSliceStart, (size_t)nSlices)) return rc;
 	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
-	ell_width_kernel<<<cdiv(((long long)nSlices + 1) * 32, 256), 256, 0, st>>>(ranges, nv, nSlices, c->pcgSliceSlots.p);
-	if (int rc = launch_exclusive_scan(c, c->pcgSliceSlots.p, nSlices + 1, c->pcgSliceStart.p, c->scanTotal.p)) return rc;
+	ell_width_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(ranges, nv, c->pcgSliceSlots.p);
+	if (int rc = launch_exclusive_scan(c, c->pcgSliceSlots.p, nSlices, c->pcgSliceStart.p, c->scanTotal.p)) return rc;
 	int totalSlots = 0;
 	MAS_CUDA(c, cudaMemcpyAsync(&totalSlots, c->scanTotal.p, sizeof(int), cudaMemcpyDeviceToHost, st));
 	MAS_CUDA(c, cudaStreamSynchronize(st));
-	if (int rc = reserve(c, c->pcgEllVal, (size_t)(totalSlots > 0 ? totalSlots : 1) * kSlotWords)) return rc;
-	ell_fill_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(diag, off, ranges, idx, nv, c->pcgSliceStart.p, c->pcgEllVal.p);
+	if (int rc = reserve(c, c->pcgEllIdx, (size_t)(totalSlots > 0 ? totalSlots : 1))) return rc;
+	if (int rc = reserve(c, c->pcgEllVal, (size_t)(totalSlots > 0 ? totalSlots : 1) * 9)) return rc;
+	ell_fill_kernel<<<cdiv((long long)nSlices * 32, 256), 256, 0, st>>>(diag, off, ranges, idx, nv, c->pcgSliceStart.p, c->pcgSliceSlots.p,
+		c->pcgEllIdx.p, c->pcgEllVal.p);
 
 	MAS_CUDA(c, cudaMemsetAsync(state, 0, sizeof(PcgState), st));
 	MAS_CUDA(c, cudaMemsetAsync(pA, 0, sizeof(double) * 4 * kMaxPartials, st));
@@ -587,8 +452,8 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
 	if (rc == MAS_OK)
 	{
-		spmv_dot_kernel<<<gridSpmv, kSpmvThreads, kSpmvSmemBytes, cap>>>(c->pcgSliceStart.p, c->pcgEllVal.p, p, Ap, nv, pA, state,
-			&state->stageErr);
+		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
+			nv, pA, state);
 		if (nStencil > 0)
 			stencil_spmv_kernel<<<gridStencil, kPcgThreads, 0, cap>>>(c->stencils.p, nStencil, p, Ap, pS, state);
 		axpy_rr_kernel<<<gridAxpy, kPcgThreads, 0, cap>>>(r, Ap, nv, pA, nStencil > 0 ? pS : nullptr, nPart, pRR, state);
@@ -620,12 +485,6 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		launched += n;
 		if (!check(c, cudaMemcpyAsync(&host, state, sizeof(PcgState), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync") ||
 			!check(c, cudaStreamSynchronize(st), "cudaStreamSynchronize")) { cudaGraphExecDestroy(exec); return MAS_ERR_CUDA; }
-		if (host.stageErr)
-		{
-			cudaGraphExecDestroy(exec);
-			c->err = "mas_pcg_solve: a bulk copy of the SpMV did not complete";
-			return MAS_ERR_CUDA;
-		}
 		if (host.done) break;
 	}
 	if (launched == 0)

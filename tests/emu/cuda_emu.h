@@ -194,7 +194,7 @@ inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_R
 // dynamic shared memory of the block being emulated (blocks run one after the other)
 inline unsigned char* emu_dynamic_smem()
 {
-	alignas(128) static unsigned char buf[224 * 1024];
+	alignas(128) static unsigned char buf[128 * 1024];
 	return buf;
 }
 inline void __threadfence_block() {}

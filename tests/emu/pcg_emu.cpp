@@ -44,20 +44,20 @@ int main()
 	// trips, the reloads inside them and the ragged last trip are all exercised
 	int grid = cdiv(cdiv(nv, kPcgThreads), 3);
 	if (grid < 1) grid = 1;
-	int gridSpmv = cdiv(cdiv(cdiv(nv, 32), kSpmvWarps), 3);                 // runs of ~3 slices per warp
+	int gridSpmv = cdiv(cdiv(cdiv(nv, 32), kPcgWarps), 3);
 	if (gridSpmv < 1) gridSpmv = 1;
-	if (const char* e = getenv("MAS_EMU_SPMV_GRID")) gridSpmv = atoi(e);   // long runs of slices per warp (the width refill every 32 slices)
 	const int nPart = grid > gridSpmv ? grid : gridSpmv;
 	const double tol2 = (double)relTol * (double)relTol;
 
 	const int nSlices = cdiv(nv, 32);
-	std::vector<int> sliceSlots((size_t)nSlices + 1), sliceStart((size_t)nSlices + 1);
-	emu::launch(cdiv(((long long)nSlices + 1) * 32, 256), 256, [&] { ell_width_kernel(ranges.data(), nv, nSlices, sliceSlots.data()); });
+	std::vector<int> sliceSlots((size_t)nSlices), sliceStart((size_t)nSlices);
+	emu::launch(cdiv((long long)nSlices * 32, 256), 256, [&] { ell_width_kernel(ranges.data(), nv, sliceSlots.data()); });
 	std::exclusive_scan(sliceSlots.begin(), sliceSlots.end(), sliceStart.begin(), 0);      // launch_exclusive_scan
-	const int totalSlots = sliceStart.back();
-	std::vector<float> ell((size_t)(totalSlots > 0 ? totalSlots : 1) * kSlotWords);
+	const int totalSlots = nSlices ? sliceStart.back() + sliceSlots.back() : 0;
+	std::vector<int> ellIdx((size_t)(totalSlots > 0 ? totalSlots : 1));
+	std::vector<float> ellVal((size_t)(totalSlots > 0 ? totalSlots : 1) * 9);
 	emu::launch(cdiv((long long)nSlices * 32, 256), 256, [&] {
-		ell_fill_kernel(diag.data(), off.data(), ranges.data(), idx.data(), nv, sliceStart.data(), ell.data());
+		ell_fill_kernel(diag.data(), off.data(), ranges.data(), idx.data(), nv, sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data());
 	});
 
 	emu::launch(cdiv(nv, 256), 256, [&] { copy_b_kernel(b.data(), r.data(), x.data(), nv); });
@@ -66,8 +66,8 @@ int main()
 	emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 0, &state); });
 	for (int it = 0; it < iterations; ++it)
 	{
-		emu::launch(gridSpmv, kSpmvThreads, [&] {
-			spmv_dot_kernel(sliceStart.data(), ell.data(), p.data(), Ap.data(), nv, pA, &state, &state.stageErr);
+		emu::launch(gridSpmv, kPcgThreads, [&] {
+			spmv_dot_kernel(sliceStart.data(), sliceSlots.data(), ellIdx.data(), ellVal.data(), p.data(), Ap.data(), nv, pA, &state);
 		});
 		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(r.data(), Ap.data(), nv, pA, nullptr, nPart, pRR, &state); });
 		emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
