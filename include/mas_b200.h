@@ -118,7 +118,12 @@ enum
 	 * the point of coherence for reads arriving over NVLink).  1: a system-scope fence precedes the flag stores, which is what
 	 * the PTX memory model guarantees between GPUs (kernel boundaries order at device scope); it costs a MEMBAR.SYS on the
 	 * latency-bound chain.  Bit-identical results either way on current NVLink hardware. */
-	MAS_OPT_STRICT_PUBLISH = 11
+	MAS_OPT_STRICT_PUBLISH = 11,
+	/* mas_pcg_solve only, default 1: for the duration of a solve the vectors of the iteration (r, z, p, Ap: 64 MB at 1M
+	 * vertices) are kept in L2 through a persisting access-policy window on every kernel of the iteration graph, while the
+	 * matrix and the packed inverses stream past them; the L2 carve-out (cudaLimitPersistingL2CacheSize, a per-device
+	 * setting) is released when the solve returns.  0: no window, no carve-out.  Results are bit-identical either way. */
+	MAS_OPT_PCG_PERSIST_L2 = 12
 };
 
 /* mas_get_int keys */

@@ -195,7 +195,7 @@ static void free_all(Context* c)
 	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
 	release(c->coarseAcc); release(c->packedInv); release(c->posTab); release(c->posTab96); release(c->invertErr);
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
-	release(c->pcgR); release(c->pcgZ); release(c->pcgP); release(c->pcgAp); release(c->pcgB); release(c->pcgX);
+	release(c->pcgR); release(c->pcgB); release(c->pcgX);
 	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);
 	release(c->pcgSliceSlots); release(c->pcgSliceStart); release(c->pcgEllIdx); release(c->pcgEllVal);
 }
@@ -296,6 +296,7 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_ALIGN_CUTS: h->optAlignCuts = value ? 1 : 0; h->hierarchyCached = false; break;
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
 	case MAS_OPT_STRICT_PUBLISH: h->optStrictPublish = value ? 1 : 0; break;
+	case MAS_OPT_PCG_PERSIST_L2: h->optPcgPersistL2 = value ? 1 : 0; break;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:

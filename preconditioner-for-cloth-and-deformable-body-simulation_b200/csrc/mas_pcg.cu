@@ -29,6 +29,8 @@
 //   latency (dependent L2 reads, two barriers) is hidden under the memory round trip instead of preceding it.
 #include "mas_internal.h"
 
+#include <vector>
+
 namespace mas {
 
 namespace {
@@ -58,6 +60,30 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
 	for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];  // every thread, same order
 	return t;
 }
+
+// the ELL image is read once per SpMV: no L1 allocation, first in line for eviction from L2 (the vectors of the iteration,
+// 16 MB each at 1M vertices, are what should stay there between the kernels)
+#ifdef MAS_CPU_EMULATION
+__device__ __forceinline__ float ell_load(const float* p) { return *p; }
+__device__ __forceinline__ int ell_load(const int* p) { return *p; }
+#else
+#ifndef MAS_L2_STREAM_HINT
+#define MAS_L2_STREAM_HINT 1
+#endif
+__device__ __forceinline__ float ell_load(const float* p)
+{
+#if MAS_L2_STREAM_HINT
+	float v;
+	unsigned long long pol;
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+	return v;
+#else
+	return *p;
+#endif
+}
+__device__ __forceinline__ int ell_load(const int* p) { return __float_as_int(ell_load(reinterpret_cast<const float*>(p))); }
+#endif
 
 // every CTA reduces the (<= kMaxPartials) partial sums of the previous pass in the same fixed order
 __device__ __forceinline__ double reduce_partials(const double* __restrict__ partials, int n, double* sh)
@@ -150,10 +176,10 @@ __global__ void __launch_bounds__(kPcgThreads) spmv_dot_kernel(const int* __rest
 			{
 				const bool in = k0 + u < width;
 				const int slot = base + 32 * (in ? k0 + u : k0);
-				c[u] = in ? ellIdx[slot + lane] : -1;
+				c[u] = in ? ell_load(ellIdx + slot + lane) : -1;
 				const float* m = ellVal + 9 * (size_t)slot + lane;
 #pragma unroll
-				for (int e = 0; e < 9; ++e) v[u][e] = in ? m[32 * e] : 0.0f;
+				for (int e = 0; e < 9; ++e) v[u][e] = in ? ell_load(m + 32 * e) : 0.0f;
 			}
 #pragma unroll
 			for (int u = 0; u < kSpmvBatch; ++u) q[u] = p[c[u] < 0 ? 0 : c[u]];
@@ -374,10 +400,9 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 {
 	cudaStream_t st = c->stream;
 	const int nv = c->nv;
-	if (int rc = reserve(c, c->pcgR, (size_t)nv)) return rc;
-	if (int rc = reserve(c, c->pcgZ, (size_t)nv)) return rc;
-	if (int rc = reserve(c, c->pcgP, (size_t)nv)) return rc;
-	if (int rc = reserve(c, c->pcgAp, (size_t)nv)) return rc;
+	// r, z, p, Ap in ONE allocation: a single L2 access-policy window covers them (see below)
+	const size_t nvPad = ((size_t)nv + 63) / 64 * 64;
+	if (int rc = reserve(c, c->pcgR, 4 * nvPad)) return rc;
 	if (int rc = reserve(c, c->pcgPartials, (size_t)4 * kMaxPartials)) return rc;
 	if (int rc = reserve(c, c->pcgState, (size_t)sizeof(PcgState))) return rc;
 	double* pA = c->pcgPartials.p;
@@ -389,7 +414,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	int gridStencil = cdiv(nStencil, kPcgThreads);
 	if (gridStencil > kMaxPartials) gridStencil = kMaxPartials;
 	PcgState* state = reinterpret_cast<PcgState*>(c->pcgState.p);
-	float4 *r = c->pcgR.p, *z = usePrecond ? c->pcgZ.p : c->pcgR.p, *p = c->pcgP.p, *Ap = c->pcgAp.p;
+	float4 *r = c->pcgR.p, *z = usePrecond ? r + nvPad : r, *p = r + 2 * nvPad, *Ap = r + 3 * nvPad;
 
 	// resident grids: occupancy x SM count, never more CTAs than there is work for
 	auto resident = [&](const void* kernel, long long workCtas) -> int {
@@ -469,11 +494,54 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;
 	// same launch priorities as the apply's own graph: the coarse chain ahead of the streaming kernels it runs beside
 	if (rc == MAS_OK && usePrecond) rc = prioritize_apply_graph(c, graph);
+	// The four vectors of the iteration (64 MB at 1M vertices) are written by one kernel and read by the next while a
+	// gigabyte of matrix and packed inverses streams through the 126 MB L2 in between.  A persisting access-policy window
+	// over them on every kernel node (hits persist, everything else is treated as streaming) keeps them on chip; the
+	// carve-out lasts for this solve only.  Only when all four fit the carve-out the device allows: a window larger than
+	// that (hit ratio < 1) thrashes - 1,051 against 784 us per iteration on the 4.2M-vertex cloth, whose vectors take 256 MB -
+	// while at 1M vertices the iteration drops from 212 to 205 us (profiles/r02_pcg_l2_persistence.txt).  Best effort: a
+	// device that refuses any of it runs as before.
+	bool persisting = false;
+	if (rc == MAS_OK)
+	{
+		int maxPersist = 0, maxWindow = 0;
+		cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+		const size_t arena = 4 * nvPad * sizeof(float4);
+		const size_t window = arena, carve = arena <= (size_t)maxPersist && arena <= (size_t)maxWindow ? arena : 0;
+		if (c->optPcgPersistL2 && carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess)
+		{
+			persisting = true;
+			cudaKernelNodeAttrValue v = {};
+			v.accessPolicyWindow.base_ptr = r;
+			v.accessPolicyWindow.num_bytes = window;
+			v.accessPolicyWindow.hitRatio = (float)((double)carve / (double)window);
+			v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			size_t n = 0;
+			cudaGraphGetNodes(graph, nullptr, &n);
+			std::vector<cudaGraphNode_t> nodes(n);
+			if (n) cudaGraphGetNodes(graph, nodes.data(), &n);
+			for (size_t i = 0; i < n; ++i)
+			{
+				cudaGraphNodeType type;
+				if (cudaGraphNodeGetType(nodes[i], &type) == cudaSuccess && type == cudaGraphNodeTypeKernel)
+					cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributeAccessPolicyWindow, &v);
+			}
+		}
+		cudaGetLastError();
+	}
 	if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
 	if (graph) cudaGraphDestroy(graph);
 	cudaStreamDestroy(cap);
-	if (rc != MAS_OK) return rc;
 
+	auto release_l2 = [&]() {
+		if (!persisting) return;
+		cudaCtxResetPersistingL2Cache();
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+		cudaGetLastError();
+	};
+	if (rc != MAS_OK) { release_l2(); return rc; }
 	PcgState host = {};
 	int launched = 0;
 	const int batch = 16;
@@ -481,10 +549,10 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	{
 		const int n = (maxIter - launched) < batch ? (maxIter - launched) : batch;
 		for (int k = 0; k < n; ++k)
-			if (!check(c, cudaGraphLaunch(exec, st), "cudaGraphLaunch")) { cudaGraphExecDestroy(exec); return MAS_ERR_CUDA; }
+			if (!check(c, cudaGraphLaunch(exec, st), "cudaGraphLaunch")) { cudaGraphExecDestroy(exec); release_l2(); return MAS_ERR_CUDA; }
 		launched += n;
 		if (!check(c, cudaMemcpyAsync(&host, state, sizeof(PcgState), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync") ||
-			!check(c, cudaStreamSynchronize(st), "cudaStreamSynchronize")) { cudaGraphExecDestroy(exec); return MAS_ERR_CUDA; }
+			!check(c, cudaStreamSynchronize(st), "cudaStreamSynchronize")) { cudaGraphExecDestroy(exec); release_l2(); return MAS_ERR_CUDA; }
 		if (host.done) break;
 	}
 	if (launched == 0)
@@ -493,6 +561,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		MAS_CUDA(c, cudaStreamSynchronize(st));
 	}
 	cudaGraphExecDestroy(exec);
+	release_l2();
 	if (itersOut) *itersOut = host.iters;
 	if (relResOut) *relResOut = host.rr0 > 0.0 ? (float)sqrt(host.rr / host.rr0) : 0.f;
 	c->pcgConverged = host.done == 1;

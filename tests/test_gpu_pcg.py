@@ -80,3 +80,7 @@ def test_pcg_device_pointers_and_determinism(pkg, synth):
     assert np.array_equal(host.x, r1.x.cpu().numpy())
     capped = pkg.pcg_solve(g, d[0], d[1], d[2], idx, b, max_iter=5)
     assert capped.iterations == 5 and not capped.converged
+    g.set_option(pkg.schwarz.OPT_PCG_PERSIST_L2, 0)                            # no persisting L2 window over r, z, p, Ap: same bits
+    plain = pkg.pcg_solve(g, d[0], d[1], d[2], idx, b)
+    torch.cuda.synchronize()
+    assert plain.iterations == r1.iterations and torch.equal(plain.x, r1.x)
