@@ -7,9 +7,9 @@
 //   diag[nv] + offdiag[nnz] column-major 3x3 blocks, CSR adjacency (ranges, idx); vectors are 16-byte xyzw.
 //   x0 = 0;  stop when ||r||_2 / ||b||_2 < relTol;  dot products in FP64 with a fixed reduction order.
 //
-// One iteration = 4 launches + the apply's own launches, captured once in a CUDA graph and replayed; the stopping test is
-// evaluated on the device (a flag turns the remaining launches of a batch into no-ops), so the host synchronises once per
-// batch of iterations, not once per iteration.  Every kernel is launched with exactly as many CTAs as are resident at once
+// One iteration = 4 launches + the apply's own launches; kIterPerGraph iterations are captured once in a CUDA graph and
+// replayed.  The stopping test and the iteration limit are evaluated on the device (a flag turns the remaining launches into
+// no-ops), so the host synchronises once per batch of graph launches, not once per iteration.  Every kernel is launched with exactly as many CTAs as are resident at once
 // (occupancy x SM count) and strides over its rows: with one CTA per 256 rows the 1M-vertex kernels ran 1.4-2.3 waves and the
 // last, partly filled wave cost 20 % of each (profiles/r02_pcg_iteration_timeline.txt).
 //   A includes the collision Hessians of the stencils of the last PreparePreconditioner (what the preconditioner was built
@@ -40,6 +40,9 @@ constexpr int kPcgThreads = 256;
 constexpr int kPcgWarps = kPcgThreads / 32;
 constexpr int kMaxPartials = 2048;  // upper bound of CTAs per reduction pass (the grids are occupancy x SM count)
 constexpr int kSpmvBatch = 4;       // block slots whose loads are in flight together in the SpMV
+constexpr int kIterPerGraph = 1;    // PCG iterations per captured graph (4: 203.4 vs 204.8 us per iteration, but up to three idle
+                                    // iterations - each still runs the apply - at the end of every solve: 20.1 vs 19.9 ms at 1M vertices)
+constexpr int kMaxBatch = 16;       // graph launches between two looks at the state
 constexpr int kVecUnroll = 4;       // elements per thread and trip of the vector kernels, loads in flight together
 
 struct PcgState
@@ -465,7 +468,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	update_p_kernel<<<gridUpdate, kPcgThreads, 0, st>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 0, state);
 	MAS_CUDA(c, cudaGetLastError());
 
-	// one iteration, captured once
+	// kIterPerGraph iterations, captured once
 	cudaGraph_t graph = nullptr;
 	cudaGraphExec_t exec = nullptr;
 	cudaStream_t cap;
@@ -475,7 +478,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	int rc = MAS_OK;
 	const int savedLaunches = c->applyLaunches;
 	if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
-	if (rc == MAS_OK)
+	for (int k = 0; k < kIterPerGraph && rc == MAS_OK; ++k)
 	{
 		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
 			nv, pA, state);
@@ -542,18 +545,26 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		cudaGetLastError();
 	};
 	if (rc != MAS_OK) { release_l2(); return rc; }
+	// The host looks at the state after every batch of launches.  Launches past the stopping test are no-ops in the PCG kernels
+	// but still run the apply (104 us each at 1M vertices), so the batch shrinks as the end comes into sight: the iterations
+	// left are extrapolated from the average contraction so far, and 60 % of them are launched.
 	PcgState host = {};
-	int launched = 0;
-	const int batch = 16;
+	int launched = 0, batch = kMaxBatch < 8 ? kMaxBatch : 8;
 	while (launched < maxIter)
 	{
-		const int n = (maxIter - launched) < batch ? (maxIter - launched) : batch;
-		for (int k = 0; k < n; ++k)
+		for (int k = 0; k < batch && launched < maxIter; ++k, launched += kIterPerGraph)
 			if (!check(c, cudaGraphLaunch(exec, st), "cudaGraphLaunch")) { cudaGraphExecDestroy(exec); release_l2(); return MAS_ERR_CUDA; }
-		launched += n;
 		if (!check(c, cudaMemcpyAsync(&host, state, sizeof(PcgState), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync") ||
 			!check(c, cudaStreamSynchronize(st), "cudaStreamSynchronize")) { cudaGraphExecDestroy(exec); release_l2(); return MAS_ERR_CUDA; }
 		if (host.done) break;
+		batch = kMaxBatch;
+		if (host.it > 0 && host.rr > 0.0 && host.rr < host.rr0)
+		{
+			const double perIter = log(host.rr / host.rr0) / host.it;            // < 0
+			const double left = (log(tol2) - log(host.rr / host.rr0)) / perIter;   // iterations until rr < tol2 rr0 at that rate
+			const int want = (int)(0.6 * left / kIterPerGraph);
+			batch = want < 1 ? 1 : want > kMaxBatch ? kMaxBatch : want;
+		}
 	}
 	if (launched == 0)
 	{
