@@ -182,7 +182,10 @@ int mas_set_option(mas_handle_t h, int key, int value);
  * (SURVEY §8e).  Must precede mas_allocate.  Default: rank 0 of 1. */
 int mas_set_partition(mas_handle_t h, int rank, int world);
 
-/* replaces m_positions/m_edges/m_faces/m_neighbours + AllocatePrecoditioner (h:44-56, cpp:38-65) */
+/* replaces m_positions/m_edges/m_faces/m_neighbours + AllocatePrecoditioner (h:44-56, cpp:38-65).
+ * One mesh per handle, as in the reference (its second call skips the allocation and the sort, cpp:44-64): a later call with
+ * the same sizes is a no-op (or a re-sort, MAS_OPT_RESORT_PERIOD); a call with OTHER sizes returns MAS_ERR_INVALID instead of
+ * carrying on with the first mesh's buffers. */
 int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces,
 	const float* positions, const int* edges, const int* faces,
 	const int* nbrStarts, const int* nbrIdx, int mem);

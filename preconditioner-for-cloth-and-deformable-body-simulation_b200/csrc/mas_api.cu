@@ -338,9 +338,12 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 	c->allocateCalls += 1;
 	if (c->allocated)
 	{
+		// The reference would carry on with the buffers and the order of the first mesh (and run out of bounds); a different
+		// mesh needs a new object.
+		if (numVerts != c->nv || numEdges != c->ne || numFaces != c->nf)
+			return fail(c, MAS_ERR_INVALID, "AllocatePrecoditioner: this object was allocated for a mesh of other sizes (one mesh per object, cpp:44-64)");
 		const bool resort = c->optResortPeriod > 0 && (c->allocateCalls - 1) % c->optResortPeriod == 0;
 		if (!resort) return MAS_OK;
-		if (numVerts != c->nv || numEdges != c->ne || numFaces != c->nf) return fail(c, MAS_ERR_INVALID, "re-sort with different sizes");
 		drop_graph(c);
 	}
 	c->nv = numVerts; c->ne = numEdges; c->nf = numFaces;

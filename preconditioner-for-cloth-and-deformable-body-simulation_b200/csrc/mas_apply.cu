@@ -488,6 +488,38 @@ __global__ void __launch_bounds__(128) solve_coarse_kernel(const float* __restri
 	solve_coarse_sum(y, coarseZ, blk, lane, warp, part);
 }
 
+// Hierarchies with at most kTopSolveBlocks coarse blocks in all (meshes up to ~8k vertices, single GPU): the restrictions above
+// level 1 and every coarse solve in ONE CTA - restrict_top_kernel's loop on 32 warps, a block barrier, then four warps per
+// coarse block as in solve_coarse_kernel.  One launch less on a chain that is nothing but launch latency at this size (64x64
+// cloth on a B200: 3.6 us against 2 x ~2 us, 10.6 -> 10.4 us per apply); the arithmetic and its order are those of the two
+// kernels it replaces.
+constexpr int kTopSolveBlocks = 8;
+constexpr int kTopSolveThreads = kTopSolveBlocks * 128;
+__global__ void __launch_bounds__(kTopSolveThreads) top_solve_kernel(const int* __restrict__ goingNext, TopArgs a, float4* __restrict__ coarseR,
+	const float* __restrict__ packed, float4* __restrict__ coarseZ, int nBlocks)
+{
+	__shared__ float part[kTopSolveBlocks][3][32][3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = kTopSolveThreads / 32;
+	for (int level = a.firstLevel; level + 1 < a.numLevel; ++level)
+	{
+		const int banks = (a.count[level] + 31) >> 5;
+		for (int bank = warp; bank < banks; bank += nWarps)
+		{
+			const int local = bank * 32 + lane;
+			float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (local < a.count[level]) rv = coarseR[a.begin[level] - a.nVC + local];
+			restrict_bank(goingNext, a.begin[level], a.count[level], bank, a.nVC, coarseR, lane, rv);
+		}
+		__threadfence_block();
+		__syncthreads();
+	}
+	const int grp = warp >> 2, w4 = warp & 3;
+	Vec3 y = { 0.f, 0.f, 0.f };
+	if (grp < nBlocks) y = solve_coarse_part(packed, coarseR, grp, lane, w4, part[grp]);
+	__syncthreads();
+	if (grp < nBlocks) solve_coarse_sum(y, coarseZ, grp, lane, w4, part[grp]);
+}
+
 // what CollectFinalZ (cpp:1698-1719) adds to every vertex below a level-1 node: Z_1 + Z_2[parent] + ...
 __global__ void prolong_sum_kernel(const float4* __restrict__ coarseZ, const int* __restrict__ goingNext, int begin1, int first,
 	int last, int nVC, int extraLevels, float4* __restrict__ zsum)
@@ -672,6 +704,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool skipProlongSum = fals
 	// already, which takes restrict_l1 — one launch — off the latency-bound chain (bit-identical, measured on a B200:
 	// together with the ancestor walk below 12.5 -> 10.5 us per apply on the 64x64 cloth)
 	const bool topFromL1 = c->world == 1 && c->numLevel > 2 && cnt1 <= 512;
+	bool fusedSolve = false;
 	if (c->numLevel > 2 && !l2x && !topFromL1)
 	{
 		restrict_l1_kernel<<<cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, 0, st>>>(c->goingNext.p, begin1, cnt1, c->nVC, 0,
@@ -693,7 +726,14 @@ static int launch_coarse(Context* c, cudaStream_t st, bool skipProlongSum = fals
 			c->applyLaunches += 1;
 			a.firstLevel = 3;
 		}
-		if (a.firstLevel + 1 < c->numLevel)
+		if (topFromL1 && nCoarseBlocks <= kTopSolveBlocks)
+		{
+			top_solve_kernel<<<1, kTopSolveThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p,
+				c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseZ.p, nCoarseBlocks);
+			c->applyLaunches += 1;
+			fusedSolve = true;
+		}
+		else if (a.firstLevel + 1 < c->numLevel)
 		{
 			restrict_top_kernel<<<1, kTopThreads, 0, st>>>(c->goingNext.p, a, c->coarseR.p);
 			c->applyLaunches += 1;
@@ -703,7 +743,7 @@ static int launch_coarse(Context* c, cudaStream_t st, bool skipProlongSum = fals
 	// redundantly on every rank, which removes any exchange of z
 	const int ownL1 = c->l1BlockEnd - c->l1BlockBegin;
 	const int solved = ownL1 + (nCoarseBlocks - c->nL1Blocks);
-	if (solved > 0)
+	if (solved > 0 && !fusedSolve)
 	{
 		solve_coarse_kernel<<<solved, 128, 0, st>>>(c->packedInv.p + (size_t)(c->ownFineEnd - c->ownFineBegin) * kTri, c->coarseR.p,
 			c->coarseZ.p, c->l1BlockBegin, ownL1, c->nL1Blocks);

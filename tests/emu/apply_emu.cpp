@@ -63,6 +63,7 @@ int main()
 		const int cnt1 = ls[2], begin1 = ls[3];
 		const int nCoarseBlocks = nCoarse / 32, nL1Blocks = pad32(cnt1) / 32;
 		const bool topFromL1 = getenv("MAS_EMU_TOP_FROM_L1") && L > 2 && cnt1 <= 512;     // small meshes
+		bool fusedSolve = false;
 		if (L > 2 && !topFromL1)
 			emu::launch(cdiv(cdiv(cnt1, 32), kWarpsPerCta), kApplyThreads, [&] {
 				restrict_l1_kernel(goingNext.data(), begin1, cnt1, nVC, 0, cdiv(cnt1, 32), coarseR.data(), nullptr, 0ull, nullptr);
@@ -81,10 +82,17 @@ int main()
 				});
 				a.firstLevel = 3;
 			}
-			if (a.firstLevel + 1 < L)
+			if (topFromL1 && nCoarseBlocks <= kTopSolveBlocks)       // launch_coarse's one-CTA kernel for tiny hierarchies
+			{
+				emu::launch(1, kTopSolveThreads, [&] {
+					top_solve_kernel(goingNext.data(), a, coarseR.data(), packed.data() + (size_t)nFine * kTri, coarseZ.data(), nCoarseBlocks);
+				});
+				fusedSolve = true;
+			}
+			else if (a.firstLevel + 1 < L)
 				emu::launch(1, kTopThreads, [&] { restrict_top_kernel(goingNext.data(), a, coarseR.data()); });
 		}
-		if (nCoarseBlocks > 0)
+		if (nCoarseBlocks > 0 && !fusedSolve)
 			emu::launch(nCoarseBlocks, 128, [&] {
 				solve_coarse_kernel(packed.data() + (size_t)nFine * kTri, coarseR.data(), coarseZ.data(), 0, nL1Blocks, nL1Blocks);
 			});

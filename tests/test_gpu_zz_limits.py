@@ -238,3 +238,47 @@ def test_graph_and_plain_launch_sequences_agree_bit_for_bit(n, gpu_cls, synth):
     g.Preconditioning(z1, r)
     torch.cuda.synchronize()
     assert torch.equal(z0, z1)
+
+
+def test_context_lifecycle_returns_all_device_memory(gpu_cls, synth, pkg):
+    """Thirty create / allocate / prepare / apply / solve / destroy cycles on meshes of changing size, some with collision
+    stencils, and an attempt to re-allocate an object for another mesh (refused): the free device memory after the last destroy equals the free memory
+    before the first create (the library owns no allocator cache), the persisting-L2 carve-out of mas_pcg_solve is released,
+    and z of the last cycle equals z of the first cycle on the same mesh (to the last bits: the coarse Galerkin sums are FP64
+    atomics whose order varies from setup to setup)."""
+    import gc
+    import torch
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    meshes = [synth.cloth(40), synth.cloth(96), synth.tet_cube(12, 12, 6)]
+    m = synth.cloth(64, with_topology=True)
+    meshes.append(synth.add_collisions(m, 40, 40, 80))
+    first = None
+    free0 = None
+    for cycle in range(31):
+        mesh = meshes[cycle % len(meshes)] if cycle < 30 else meshes[0]
+        g = gpu_cls(0).setup_from_mesh(mesh)
+        r = synth.residual(mesh.nv)
+        z = np.zeros_like(r)
+        g.Preconditioning(z, r)
+        if cycle % 3 == 0:
+            res = pkg.pcg_solve(g, mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.nbr_idx, r, max_iter=12)
+            assert res.iterations > 0
+        if cycle % 4 == 1:                                     # a mesh of other sizes on the same object is refused, not run
+            other = meshes[(cycle + 1) % len(meshes)]
+            with pytest.raises(pkg.MasError, match="one mesh per object"):
+                g.setup_from_mesh(other)
+            z2 = np.zeros_like(r)
+            g.Preconditioning(z2, r)                            # ... and the object still serves its own mesh
+            assert np.array_equal(z2, z)
+        if cycle == 0:
+            first = z.copy()
+        g.close()
+        del g
+        gc.collect()
+        torch.cuda.synchronize()
+        if cycle == 0:
+            free0 = torch.cuda.mem_get_info()[0]                # after one full cycle: CUDA's own lazily created state is in place
+    assert np.linalg.norm(z - first) <= 1e-6 * np.linalg.norm(first)
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 <= 4 << 20, (free0, free1)             # nothing accumulates (allow 4 MiB for allocator granularity)
