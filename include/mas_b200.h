@@ -122,7 +122,7 @@ enum
 	/* mas_pcg_solve only, default 1: for the duration of a solve the vectors of the iteration (r, z, p, Ap: 64 MB at 1M
 	 * vertices) are kept in L2 through a persisting access-policy window on every kernel of the iteration graph, while the
 	 * matrix and the packed inverses stream past them; the L2 carve-out (cudaLimitPersistingL2CacheSize, a per-device
-	 * setting) is released when the solve returns.  0: no window, no carve-out.  Results are bit-identical either way. */
+	 * setting; the value found is restored) is released when the solve returns.  0: no window, no carve-out.  Results are bit-identical either way. */
 	MAS_OPT_PCG_PERSIST_L2 = 12
 };
 

@@ -505,6 +505,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	// while at 1M vertices the iteration drops from 212 to 205 us (profiles/r02_pcg_l2_persistence.txt).  Best effort: a
 	// device that refuses any of it runs as before.
 	bool persisting = false;
+	size_t l2LimitBefore = 0;   // the application's own carve-out, restored when the solve returns
 	if (rc == MAS_OK)
 	{
 		int maxPersist = 0, maxWindow = 0;
@@ -512,7 +513,9 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
 		const size_t arena = 4 * nvPad * sizeof(float4);
 		const size_t window = arena, carve = arena <= (size_t)maxPersist && arena <= (size_t)maxWindow ? arena : 0;
-		if (c->optPcgPersistL2 && carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess)
+		if (cudaDeviceGetLimit(&l2LimitBefore, cudaLimitPersistingL2CacheSize) != cudaSuccess) l2LimitBefore = 0;
+		if (c->optPcgPersistL2 && carve > 0 &&
+			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve > l2LimitBefore ? carve : l2LimitBefore) == cudaSuccess)
 		{
 			persisting = true;
 			cudaKernelNodeAttrValue v = {};
@@ -541,7 +544,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	auto release_l2 = [&]() {
 		if (!persisting) return;
 		cudaCtxResetPersistingL2Cache();
-		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+		cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, l2LimitBefore);
 		cudaGetLastError();
 	};
 	if (rc != MAS_OK) { release_l2(); return rc; }

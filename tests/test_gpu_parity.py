@@ -35,6 +35,8 @@ def _cases(synth):
         "chain32_exactly_one_bank": lambda: synth.chain(32),
         "chain33_one_over": lambda: synth.chain(33),
         "chain100_fragmented_banks": lambda: synth.chain(100),    # bent line: many components per Morton bank
+        "cloth32_level1_fills_one_bank": lambda: synth.cloth(32),  # 1,024 verts = 32 fine banks: level 1 is exactly one bank
+        "cloth33_level1_one_over": lambda: synth.cloth(33),       # 1,089 verts: 35 fine banks, level 1 spills into a second bank
         # folded sheet with the EF / EE / VF stencils of the proximity producer (collide.py, run on the GPU here)
         "folded64_proximity": lambda: _collide().proximity_stencils(synth.folded_cloth(64, 64), radius=0.006),
     }
@@ -48,7 +50,7 @@ def _collide():
 CASE_NAMES = ["cloth64", "cloth50_ragged", "cloth7_tiny", "cloth5_single_bank", "cloth64_skew", "cloth96_collisions",
               "cloth128_dense_collisions", "tet16x16x8", "cloth200_stiff", "cloth_rect96x40", "cloth20_isolated_vertices",
               "chain1_single_vertex", "chain32_exactly_one_bank", "chain33_one_over", "chain100_fragmented_banks",
-              "folded64_proximity"]
+              "cloth32_level1_fills_one_bank", "cloth33_level1_one_over", "folded64_proximity"]
 
 
 @pytest.fixture(scope="module")

@@ -282,3 +282,28 @@ def test_context_lifecycle_returns_all_device_memory(gpu_cls, synth, pkg):
     assert np.linalg.norm(z - first) <= 1e-6 * np.linalg.norm(first)
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 <= 4 << 20, (free0, free1)             # nothing accumulates (allow 4 MiB for allocator granularity)
+
+
+def test_stencil_counts_grow_and_shrink_between_prepares(gpu_cls, synth):
+    """One object, PreparePreconditioner with few, then eight times as many, then few collision stencils again (the stencil
+    buffers grow on the way): every z equals that of a fresh object prepared once with the same input."""
+    def coll(frac):
+        m = synth.cloth(96, with_topology=True)
+        return synth.add_collisions(m, m.nv // (4 * frac), m.nv // (4 * frac), m.nv // (2 * frac))
+    few, many = coll(8), coll(1)
+    assert many.ef_total >= 8 * few.ef_total > 0
+    r = synth.residual(few.nv)
+
+    def prepare_apply(g, mesh):
+        g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.ef, mesh.ee, mesh.vf, mesh.ef_total, mesh.ee_total,
+                                mesh.vf_total)
+        z = np.zeros_like(r)
+        g.Preconditioning(z, r)
+        return z, g.stencil_num, g.level_size().copy()
+    g = gpu_cls(0).setup_from_mesh(few)
+    for mesh in (few, many, few, many):
+        z, n, levels = prepare_apply(g, mesh)
+        z1, n1, levels1 = prepare_apply(gpu_cls(0).setup_from_mesh(mesh), mesh)
+        # (the reference keeps only the stencils that pass its own filters: fewer than the totals handed in)
+        assert 0 < n == n1 <= mesh.ef_total + mesh.ee_total + mesh.vf_total and np.array_equal(levels, levels1)
+        assert np.abs(z - z1).max() <= 1e-6 * np.abs(z1).max()
