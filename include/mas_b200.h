@@ -123,12 +123,7 @@ enum
 	 * vertices) are kept in L2 through a persisting access-policy window on every kernel of the iteration graph, while the
 	 * matrix and the packed inverses stream past them; the L2 carve-out (cudaLimitPersistingL2CacheSize, a per-device
 	 * setting; the value found is restored) is released when the solve returns.  0: no window, no carve-out.  Results are bit-identical either way. */
-	MAS_OPT_PCG_PERSIST_L2 = 12,
-	/* mas_pcg_solve only, default 1: the iteration graph is the body of a conditional WHILE node whose condition the last
-	 * kernel of the iteration sets on the device (stopping test or iteration limit): one graph launch and one
-	 * synchronisation per solve, no iteration past the stopping test.  0: the host launches batches of iteration graphs and
-	 * reads the state back after each batch.  Same iterates either way. */
-	MAS_OPT_PCG_DEVICE_LOOP = 13
+	MAS_OPT_PCG_PERSIST_L2 = 12
 };
 
 /* mas_get_int keys */

@@ -297,7 +297,6 @@ int mas_set_option(mas_handle_t h, int key, int value)
 	case MAS_OPT_CACHE_HIERARCHY: h->optCacheHierarchy = value ? 1 : 0; return MAS_OK;
 	case MAS_OPT_STRICT_PUBLISH: h->optStrictPublish = value ? 1 : 0; break;
 	case MAS_OPT_PCG_PERSIST_L2: h->optPcgPersistL2 = value ? 1 : 0; break;
-	case MAS_OPT_PCG_DEVICE_LOOP: h->optPcgDeviceLoop = value ? 1 : 0; break;
 	case MAS_OPT_STENCIL_FIX: h->optStencilFix = value ? 1 : 0; break;
 	case MAS_OPT_RESORT_PERIOD: h->optResortPeriod = value > 0 ? value : 0; break;
 	case MAS_OPT_INVERT_VARIANT:

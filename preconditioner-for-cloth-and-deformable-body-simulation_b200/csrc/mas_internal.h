@@ -99,7 +99,6 @@ struct Context
 	int optResortPeriod = 0;     // > 0: every that many mas_allocate calls the Morton order is rebuilt (0: once per object, Q1)
 	int optInvertVariant = 0;    // 0: tcgen05 tensor-core inversion (3xTF32 block Gauss-Jordan); 1: FP32 CUDA-core blocked LDL^T
 	int optHostPull = 0;         // host-pointer apply: 1 pull a page-locked residual with a kernel instead of the copy engine, 2 pick the faster
-	int optPcgDeviceLoop = 1;    // mas_pcg_solve: the iteration graph is the body of a conditional WHILE node
 	int optPcgPersistL2 = 1;     // mas_pcg_solve: persisting L2 window over the vectors of the iteration
 	int optStrictPublish = 0;    // 1: system-scope fence before the peer flag stores of the sharded apply
 	int optCacheHierarchy = 1;   // 1: a collision-free prepare reuses the clustering of the previous collision-free prepare

@@ -8,11 +8,8 @@
 //   x0 = 0;  stop when ||r||_2 / ||b||_2 < relTol;  dot products in FP64 with a fixed reduction order.
 //
 // One iteration = 4 launches + the apply's own launches; kIterPerGraph iterations are captured once in a CUDA graph and
-// replayed.  The stopping test and the iteration limit are evaluated on the device.  By default the iteration graph is the
-// body of a conditional WHILE node (CUDA 12.4 graphs) whose condition update_p's last CTA sets: the whole solve is ONE graph
-// launch and one synchronisation, and no iteration runs past the stopping test.  Without it (MAS_OPT_PCG_DEVICE_LOOP = 0, or
-// a driver that refuses the node) the host launches batches of iteration graphs and looks at the state after each batch; a
-// flag turns the launches past the stopping test into no-ops in the PCG kernels (the apply still runs).  Every kernel is launched with exactly as many CTAs as are resident at once
+// replayed.  The stopping test and the iteration limit are evaluated on the device (a flag turns the remaining launches into
+// no-ops), so the host synchronises once per batch of graph launches, not once per iteration.  Every kernel is launched with exactly as many CTAs as are resident at once
 // (occupancy x SM count) and strides over its rows: with one CTA per 256 rows the 1M-vertex kernels ran 1.4-2.3 waves and the
 // last, partly filled wave cost 20 % of each (profiles/r02_pcg_iteration_timeline.txt).
 //   A includes the collision Hessians of the stencils of the last PreparePreconditioner (what the preconditioner was built
@@ -318,30 +315,16 @@ __global__ void __launch_bounds__(kPcgThreads) dot_kernel(const float4* __restri
 	if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
-__device__ __forceinline__ void set_loop_condition(cudaGraphConditionalHandle loop, unsigned value)
-{
-#ifndef MAS_CPU_EMULATION
-	cudaGraphSetConditional(loop, value);
-#else
-	(void)loop; (void)value;
-#endif
-}
-
 // mode 0 (setup): rr0 = rr = sum(rrPartials), rz = sum(rzPartials), p = z, it = 0
 // mode 1 (iteration): x += alpha p, beta = rz'/rz, p = z + beta p; the last CTA records rr, the stopping test and the
 // iteration count.  The flag written here is read only by LATER launches, so all CTAs of one launch see the same value.
 __global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restrict__ x, float4* __restrict__ p, const float4* __restrict__ z,
 	int nv, const double* __restrict__ rzPartials, const double* __restrict__ rrPartials, int nPartials, double tol2, int maxIter,
-	int mode, PcgState* stw, cudaGraphConditionalHandle loop, int useLoop)
+	int mode, PcgState* stw)
 {
 	__shared__ double sh[2 * kPcgWarps];
 	volatile PcgState* st = stw;
-	if (st->done)
-	{
-		// (a solve that was finished before its first iteration: end the device-side loop)
-		if (useLoop && blockIdx.x == 0 && threadIdx.x == 0) set_loop_condition(loop, 0u);
-		return;
-	}
+	if (st->done) return;
 	const int stride = gridDim.x * blockDim.x;
 	int i0 = blockIdx.x * blockDim.x + threadIdx.x;
 	float4 zv[kVecUnroll], pv[kVecUnroll], xv[kVecUnroll];
@@ -398,8 +381,6 @@ __global__ void __launch_bounds__(kPcgThreads) update_p_kernel(float4* __restric
 			st->iters = st->it;
 			if (rr < tol2 * st->rr0) st->done = 1;
 			else if (st->it >= maxIter) st->done = 2;
-			// the iteration graph is the body of a WHILE node: run it again unless this iteration ended the solve
-			if (useLoop) set_loop_condition(loop, st->done ? 0u : 1u);
 		}
 		__threadfence();
 	}
@@ -484,7 +465,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	if (int rc = precondition()) return rc;
 	dot_kernel<<<gridAxpy, kPcgThreads, 0, st>>>(r, r, nv, pRR, state);   // pRR always holds gridAxpy partials (axpy_rr refills it)
 	dot_kernel<<<gridDot, kPcgThreads, 0, st>>>(r, z, nv, pRZ, state);
-	update_p_kernel<<<gridUpdate, kPcgThreads, 0, st>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 0, state, 0, 0);
+	update_p_kernel<<<gridUpdate, kPcgThreads, 0, st>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 0, state);
 	MAS_CUDA(c, cudaGetLastError());
 
 	// kIterPerGraph iterations, captured once
@@ -496,33 +477,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	c->stream = cap;
 	int rc = MAS_OK;
 	const int savedLaunches = c->applyLaunches;
-	// device-side loop: outer graph = one conditional WHILE node, the iteration is captured into its body graph
-	bool deviceLoop = c->optPcgDeviceLoop != 0 && maxIter > 0;
-	cudaGraph_t outer = nullptr, body = nullptr;
-	cudaGraphConditionalHandle loop = 0;
-	if (deviceLoop)
-	{
-		cudaGraphNodeParams np = { cudaGraphNodeTypeConditional };
-		cudaGraphNode_t node;
-		deviceLoop = cudaGraphCreate(&outer, 0) == cudaSuccess &&
-			cudaGraphConditionalHandleCreate(&loop, outer, 1, cudaGraphCondAssignDefault) == cudaSuccess;
-		if (deviceLoop)
-		{
-			np.conditional.handle = loop;
-			np.conditional.type = cudaGraphCondTypeWhile;
-			np.conditional.size = 1;
-			deviceLoop = cudaGraphAddNode(&node, outer, nullptr, 0, &np) == cudaSuccess;
-			if (deviceLoop) body = np.conditional.phGraph_out[0];
-		}
-		if (!deviceLoop)
-		{
-			if (outer) cudaGraphDestroy(outer);
-			outer = nullptr;
-			cudaGetLastError();
-		}
-	}
-	if (!check(c, deviceLoop ? cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)
-	                         : cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
+	if (!check(c, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture")) rc = MAS_ERR_CUDA;
 	for (int k = 0; k < kIterPerGraph && rc == MAS_OK; ++k)
 	{
 		spmv_dot_kernel<<<gridSpmv, kPcgThreads, 0, cap>>>(c->pcgSliceStart.p, c->pcgSliceSlots.p, c->pcgEllIdx.p, c->pcgEllVal.p, p, Ap,
@@ -533,7 +488,7 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		c->applyLaunches = 0;
 		if (usePrecond) rc = apply_forked(c, r, z, cap);   // coarse chain concurrent with the head of the fine solve
 		dot_kernel<<<gridDot, kPcgThreads, 0, cap>>>(r, z, nv, pRZ, state);
-		update_p_kernel<<<gridUpdate, kPcgThreads, 0, cap>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 1, state, loop, deviceLoop ? 1 : 0);
+		update_p_kernel<<<gridUpdate, kPcgThreads, 0, cap>>>(x, p, z, nv, pRZ, pRR, nPart, tol2, maxIter, 1, state);
 	}
 	c->pcgLaunchesPerIter = 4 + (nStencil > 0 ? 1 : 0) + (usePrecond ? c->applyLaunches : 0);
 	c->applyLaunches = savedLaunches;
@@ -582,9 +537,8 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 		}
 		cudaGetLastError();
 	}
-	if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&exec, deviceLoop ? outer : graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
-	if (deviceLoop) cudaGraphDestroy(outer);   // (owns the body graph the capture went into)
-	else if (graph) cudaGraphDestroy(graph);
+	if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&exec, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
+	if (graph) cudaGraphDestroy(graph);
 	cudaStreamDestroy(cap);
 
 	auto release_l2 = [&]() {
@@ -599,13 +553,6 @@ int pcg_solve(Context* c, const float* diag, const float* off, const int* ranges
 	// left are extrapolated from the average contraction so far, and 60 % of them are launched.
 	PcgState host = {};
 	int launched = 0, batch = kMaxBatch < 8 ? kMaxBatch : 8;
-	if (deviceLoop)
-	{
-		if (!check(c, cudaGraphLaunch(exec, st), "cudaGraphLaunch") ||
-			!check(c, cudaMemcpyAsync(&host, state, sizeof(PcgState), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync") ||
-			!check(c, cudaStreamSynchronize(st), "cudaStreamSynchronize")) { cudaGraphExecDestroy(exec); release_l2(); return MAS_ERR_CUDA; }
-		launched = maxIter;
-	}
 	while (launched < maxIter)
 	{
 		for (int k = 0; k < batch && launched < maxIter; ++k, launched += kIterPerGraph)

@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("MAS_B200_LIB") or os.path.join(_HERE, "libmas_b200.so
 MAS_MEM_HOST, MAS_MEM_DEVICE = 0, 1
 (OPT_PROLONG_ALL_LEVELS, OPT_APPLY_VARIANT, OPT_USE_GRAPH, OPT_TIME_KERNELS, OPT_ALIGN_CUTS, OPT_STENCIL_FIX,
  OPT_RESORT_PERIOD, OPT_HOST_PULL, OPT_INVERT_VARIANT, OPT_REGISTER_HOST, OPT_CACHE_HIERARCHY, OPT_STRICT_PUBLISH,
- OPT_PCG_PERSIST_L2, OPT_PCG_DEVICE_LOOP) = range(14)
+ OPT_PCG_PERSIST_L2) = range(13)
 (INT_NUM_VERTS, INT_NUM_LEVEL, INT_TOTAL_CLUSTERS, INT_NUM_BLOCKS, INT_STENCIL_NUM, INT_NNZ, INT_APPLY_LAUNCHES,
  INT_PACKED_FLOATS_PER_BLOCK, INT_OWNED_BLOCK_BEGIN, INT_OWNED_BLOCK_END, INT_PREPARE_LAUNCHES, INT_PCG_LAUNCHES_PER_ITER,
  INT_PCG_CONVERGED, INT_PEER_ERROR, INT_ALIGNED_CUTS, INT_HOST_PULL_CHOICE, INT_HOST_BYTES_IN, INT_HOST_BYTES_OUT) = range(18)

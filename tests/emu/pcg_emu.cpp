@@ -63,7 +63,7 @@ int main()
 	emu::launch(cdiv(nv, 256), 256, [&] { copy_b_kernel(b.data(), r.data(), x.data(), nv); });
 	emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), r.data(), nv, pRR, &state); });
 	emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
-	emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 0, &state, 0, 0); });
+	emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 0, &state); });
 	for (int it = 0; it < iterations; ++it)
 	{
 		emu::launch(gridSpmv, kPcgThreads, [&] {
@@ -71,7 +71,7 @@ int main()
 		});
 		emu::launch(grid, kPcgThreads, [&] { axpy_rr_kernel(r.data(), Ap.data(), nv, pA, nullptr, nPart, pRR, &state); });
 		emu::launch(grid, kPcgThreads, [&] { dot_kernel(r.data(), z, nv, pRZ, &state); });
-		emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 1, &state, 0, 0); });
+		emu::launch(grid, kPcgThreads, [&] { update_p_kernel(x.data(), p.data(), z, nv, pRZ, pRR, nPart, tol2, iterations, 1, &state); });
 	}
 	fwrite(x.data(), 16, (size_t)nv, stdout);
 	fwrite(r.data(), 16, (size_t)nv, stdout);

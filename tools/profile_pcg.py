@@ -14,8 +14,6 @@ g.AllocatePrecoditioner(mesh.nv, 0, 0)
 g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts)
 b = torch.from_numpy(S.residual(mesh.nv)).cuda()
 it = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-if os.environ.get("MAS_PCG_DEVICE_LOOP") is not None:
-    g.set_option(13, int(os.environ["MAS_PCG_DEVICE_LOOP"]))
 if os.environ.get("MAS_PCG_PERSIST_L2") is not None:
     g.set_option(12, int(os.environ["MAS_PCG_PERSIST_L2"]))
 solve = lambda: pkg.pcg_solve(g, mesh.diag, mesh.offdiag, mesh.nbr_starts, mesh.nbr_idx, b, max_iter=it)
