@@ -307,3 +307,34 @@ def test_stencil_counts_grow_and_shrink_between_prepares(gpu_cls, synth):
         # (the reference keeps only the stencils that pass its own filters: fewer than the totals handed in)
         assert 0 < n == n1 <= mesh.ef_total + mesh.ee_total + mesh.vf_total and np.array_equal(levels, levels1)
         assert np.abs(z - z1).max() <= 1e-6 * np.abs(z1).max()
+
+
+@pytest.mark.parametrize("n", [64, 512])
+def test_three_thousand_graph_replays_are_bit_identical(n, gpu_cls, synth):
+    """Soak: 3,000 back-to-back applies of the captured graph (coarse chain, head, tail and coarse addition overlap inside it),
+    alternating between two residuals and two output buffers: every z equals the first z of its residual bit for bit, and
+    nothing of one apply leaks into the next."""
+    import torch
+    mesh = synth.cloth_rect_device(n, n, torch.device("cuda:0"))
+    g = gpu_cls(0)
+    g.m_positions, g.m_neighbours = mesh.positions, (mesh.nbr_starts, mesh.nbr_idx)
+    g.AllocatePrecoditioner(mesh.nv, 0, 0)
+    g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts)
+    ra = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+    rb = torch.flip(ra, dims=[0]).contiguous() * 3.0
+    za, zb = torch.empty_like(ra), torch.empty_like(ra)
+    g.Preconditioning(za, ra)
+    g.Preconditioning(zb, rb)
+    torch.cuda.synchronize()
+    first_a, first_b = za.clone(), zb.clone()
+    assert not torch.equal(first_a, first_b)
+    bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    for k in range(1500):
+        za.fill_(float("nan"))
+        g.Preconditioning(za, ra)
+        bad += (za != first_a).any().long()
+        zb.fill_(float("nan"))
+        g.Preconditioning(zb, rb)
+        bad += (zb != first_b).any().long()
+    torch.cuda.synchronize()
+    assert int(bad) == 0
