@@ -427,15 +427,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_per_step = float(tms.item()) / args.steps
-    if rank == 0:
-        # hold the load a little longer so the 50 ms sampler sees the clocks under load
-        t_end = time.perf_counter() + 0.4
-    else:
-        t_end = 0
-    while world == 1 and not args.lean and time.perf_counter() < t_end:
-        for _ in range(50):
+    if not args.lean:
+        # hold the load ~0.4 s longer so that the 50 ms sampler sees the clocks under load (the timed region of 200 applies
+        # lasts 21 ms).  Every rank runs the same number of extra steps: ms_per_step is the all-reduced maximum.
+        for _ in range(int(min(20000, max(50, 400.0 / max(ms_per_step, 1e-3))))):
             step()
-        torch.cuda.synchronize()
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = g.apply_launches
 
