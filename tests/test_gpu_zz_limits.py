@@ -338,3 +338,42 @@ def test_three_thousand_graph_replays_are_bit_identical(n, gpu_cls, synth):
         bad += (zb != first_b).any().long()
     torch.cuda.synchronize()
     assert int(bad) == 0
+
+
+def test_two_contexts_on_one_gpu_from_two_host_threads(gpu_cls, synth, pkg):
+    """The library keeps no state outside its handles: two objects driven at the same time from two host threads, each on a
+    stream of its own (different meshes, setup + 200 applies + a PCG solve), give what each gives alone."""
+    import threading
+    import torch
+    meshes = [synth.cloth(96), synth.tet_cube(16, 16, 8)]
+
+    def run(mesh, stream, out, key):
+        try:
+            with torch.cuda.stream(stream):
+                g = gpu_cls(0, stream=stream).setup_from_mesh(mesh, device_inputs=True)
+                r = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+                z = torch.empty_like(r)
+                for _ in range(200):
+                    g.Preconditioning(z, r)
+                d = g._dev_inputs
+                res = pkg.pcg_solve(g, d[0], d[1], d[2], torch.from_numpy(mesh.nbr_idx).cuda(), r, rel_tol=1e-4)
+                stream.synchronize()
+                out[key] = (z.cpu().numpy(), res.iterations, res.x.cpu().numpy())
+                g.close()
+        except Exception as e:                                   # surfaced by the assertion below
+            out[key] = e
+    alone, together = {}, {}
+    for i, mesh in enumerate(meshes):
+        run(mesh, torch.cuda.Stream(), alone, i)
+    threads = [threading.Thread(target=run, args=(mesh, torch.cuda.Stream(), together, i)) for i, mesh in enumerate(meshes)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for i in range(len(meshes)):
+        assert not isinstance(alone[i], Exception), alone[i]
+        assert not isinstance(together[i], Exception), together[i]
+        # (setup sums its coarse Galerkin terms with FP64 atomics: two setups of one mesh agree to rounding, not bit for bit)
+        assert np.abs(together[i][0] - alone[i][0]).max() <= 1e-6 * np.abs(alone[i][0]).max()
+        assert abs(together[i][1] - alone[i][1]) <= 1
+        assert np.linalg.norm(together[i][2] - alone[i][2]) <= 1e-3 * np.linalg.norm(alone[i][2])
