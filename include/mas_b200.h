@@ -196,7 +196,8 @@ int mas_prepare(mas_handle_t h, const float* diagonal, const float* csrOffDiagon
 	const void* efSets, const void* eeSets, const void* vfSets,
 	unsigned efTotal, unsigned eeTotal, unsigned vfTotal, int mem);
 
-/* replaces Preconditioning (h:63, cpp:100-110); `dim` is unused there and dropped here */
+/* replaces Preconditioning (h:63, cpp:100-110); `dim` is unused there and dropped here.  z == residual (in place) works with
+ * host pointers as it does in the reference; with device pointers overlapping z and residual return MAS_ERR_INVALID. */
 int mas_apply(mas_handle_t h, float* z, const float* residual, int mem);
 
 /* Multi-GPU (world > 1) phase split.  Between *_begin and *_end the caller sums the exchange

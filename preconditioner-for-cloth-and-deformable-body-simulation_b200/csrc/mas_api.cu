@@ -522,7 +522,15 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 		return fail(c, MAS_ERR_INVALID, "sharded context: attach the peers (mas_peer_attach) or use mas_apply_begin / exchange / mas_apply_end");
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	if (int rc = peer_failed(c)) return rc;        // sticky: an earlier apply lost a peer
-	if (mem == MAS_MEM_DEVICE) return run_apply_device(c, (const float4*)residual, (float4*)z);
+	if (mem == MAS_MEM_DEVICE)
+	{
+		// the level-0 solve writes z while other kernels of the same graph still read r (host pointers are staged through
+		// separate device buffers, so an in-place call works there as it does in the reference)
+		const char* zb = (const char*)z; const char* rb = (const char*)residual;
+		const size_t bytes = sizeof(float4) * (size_t)c->nv;
+		if (zb < rb + bytes && rb < zb + bytes) return fail(c, MAS_ERR_INVALID, "mas_apply: z and residual overlap in device memory");
+		return run_apply_device(c, (const float4*)residual, (float4*)z);
+	}
 	if (int rc = reserve(c, c->rIn, (size_t)c->nv)) return rc;
 	if (int rc = reserve(c, c->zOut, (size_t)c->nv)) return rc;
 	if (c->optRegisterHost)
@@ -576,7 +584,6 @@ int mas_apply(mas_handle_t h, float* z, const float* residual, int mem)
 		MAS_CUDA(c, cudaMemcpyAsync(c->rIn.p, residual, sizeof(float4) * (size_t)c->nv, cudaMemcpyHostToDevice, c->stream));
 	if (sampling) MAS_CUDA(c, cudaEventRecord(c->evS1, c->stream));
 	if (int rc = run_apply_device(c, c->rIn.p, c->zOut.p)) return rc;
-	// a shard only produces its own vertices' z; copy everything, the caller merges shards
 	MAS_CUDA(c, cudaMemcpyAsync(z, c->zOut.p, sizeof(float4) * (size_t)c->nv, cudaMemcpyDeviceToHost, c->stream));
 	MAS_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (sampling)
@@ -610,6 +617,11 @@ int mas_apply_end(mas_handle_t h, float* z, int mem)
 	if (!h || !z) return MAS_ERR_INVALID;
 	Context* c = h;
 	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
+	{
+		const char* zb = (const char*)z; const char* rb = (const char*)c->graphR;
+		const size_t bytes = sizeof(float4) * (size_t)c->nv;
+		if (rb && zb < rb + bytes && rb < zb + bytes) return fail(c, MAS_ERR_INVALID, "mas_apply_end: z and residual overlap in device memory");
+	}
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	c->phaseSplit = true;
 	const int rc = apply_end(c, (const float4*)c->graphR, (float4*)z);

@@ -343,6 +343,17 @@ def test_errors_are_reported_not_swallowed(gpu_cls, synth, pkg):
     with pytest.raises(pkg.MasError):
         g.PreparePreconditioner(mesh.diag, mesh.offdiag, mesh.nbr_starts)     # before Allocate
     g.setup_from_mesh(mesh)
+    # in place: fine with host pointers (as in the reference, which reads the residual before it writes z), refused with device
+    # pointers (the level-0 solve writes z while the restriction still reads r)
+    import torch
+    r = synth.residual(mesh.nv)
+    z = g.Preconditioning(np.zeros_like(r), r)
+    inplace = r.copy()
+    g.Preconditioning(inplace, inplace)
+    assert np.array_equal(inplace, z)
+    rd = torch.from_numpy(r).cuda()
+    with pytest.raises(pkg.MasError, match="overlap"):
+        g.Preconditioning(rd, rd)
     with pytest.raises(pkg.MasError):
         g.Preconditioning(np.zeros((mesh.nv, 4), np.float64), synth.residual(mesh.nv))
 
