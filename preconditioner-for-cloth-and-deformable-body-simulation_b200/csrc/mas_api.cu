@@ -139,13 +139,11 @@ static void register_host_range(Context* c, const void* p, size_t bytes)
 
 static void drop_graph(Context* c)
 {
-	if (c->applyGraph)
+	for (Context::ApplyGraphSlot& g : c->applyGraphs)
 	{
-		cudaGraphExecDestroy(c->applyGraph);
-		c->applyGraph = nullptr;
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+		g = Context::ApplyGraphSlot();
 	}
-	c->graphR = nullptr;
-	c->graphZ = nullptr;
 }
 
 static void close_peers(Context* c)
@@ -482,9 +480,16 @@ static int run_apply_device(Context* c, const float4* r, float4* z)
 		if (c->optTimeKernels) MAS_CUDA(c, cudaEventRecord(c->evAp1, c->stream));
 		return MAS_OK;
 	}
-	if (!c->applyGraph || c->graphR != (const float*)r || c->graphZ != (float*)z)
+	Context::ApplyGraphSlot* slot = nullptr;
+	for (Context::ApplyGraphSlot& g : c->applyGraphs)
+		if (g.exec && g.r == (const float*)r && g.z == (float*)z) slot = &g;
+	if (!slot)
 	{
-		drop_graph(c);
+		slot = &c->applyGraphs[0];
+		for (Context::ApplyGraphSlot& g : c->applyGraphs)
+			if (!g.exec || (slot->exec && g.lastUse < slot->lastUse)) slot = &g;
+		if (slot->exec) cudaGraphExecDestroy(slot->exec);
+		*slot = Context::ApplyGraphSlot();
 		// the capture origin carries the latency-bound coarse chain: highest priority, so that its CTAs are dispatched ahead of
 		// the queued fine-level CTAs of the concurrent branch (kernel nodes inherit the capturing stream's priority)
 		cudaStream_t cap;
@@ -502,14 +507,15 @@ static int run_apply_device(Context* c, const float4* r, float4* z)
 		c->stream = saved;
 		if (rc == MAS_OK && !check(c, e, "cudaStreamEndCapture")) rc = MAS_ERR_CUDA;
 		if (rc == MAS_OK) rc = prioritize_apply_graph(c, graph);
-		if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&c->applyGraph, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
+		if (rc == MAS_OK && !check(c, cudaGraphInstantiate(&slot->exec, graph, 0), "cudaGraphInstantiate")) rc = MAS_ERR_CUDA;
 		if (graph) cudaGraphDestroy(graph);
 		cudaStreamDestroy(cap);
-		if (rc != MAS_OK) { c->applyGraph = nullptr; return rc; }
-		c->graphR = (const float*)r;
-		c->graphZ = (float*)z;
+		if (rc != MAS_OK) { slot->exec = nullptr; return rc; }
+		slot->r = (const float*)r;
+		slot->z = (float*)z;
 	}
-	MAS_CUDA(c, cudaGraphLaunch(c->applyGraph, c->stream));
+	slot->lastUse = ++c->applyGraphClock;
+	MAS_CUDA(c, cudaGraphLaunch(slot->exec, c->stream));
 	return MAS_OK;
 }
 
@@ -604,7 +610,7 @@ int mas_apply_begin(mas_handle_t h, const float* residual, int mem)
 	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	c->applyLaunches = 0;
-	c->graphR = residual;
+	c->phaseR = residual;
 	// the caller sums the exchange buffer between _begin and _end: attached peers play no part in this protocol
 	c->phaseSplit = true;
 	const int rc = apply_begin(c, (const float4*)residual);
@@ -618,13 +624,14 @@ int mas_apply_end(mas_handle_t h, float* z, int mem)
 	Context* c = h;
 	if (mem != MAS_MEM_DEVICE) return fail(c, MAS_ERR_INVALID, "phase-split apply takes device pointers");
 	{
-		const char* zb = (const char*)z; const char* rb = (const char*)c->graphR;
+		const char* zb = (const char*)z; const char* rb = (const char*)c->phaseR;
 		const size_t bytes = sizeof(float4) * (size_t)c->nv;
 		if (rb && zb < rb + bytes && rb < zb + bytes) return fail(c, MAS_ERR_INVALID, "mas_apply_end: z and residual overlap in device memory");
 	}
+	if (!c->phaseR) return fail(c, MAS_ERR_INVALID, "mas_apply_begin first");
 	MAS_CUDA(c, cudaSetDevice(c->device));
 	c->phaseSplit = true;
-	const int rc = apply_end(c, (const float4*)c->graphR, (float4*)z);
+	const int rc = apply_end(c, (const float4*)c->phaseR, (float4*)z);
 	c->phaseSplit = false;
 	return rc;
 }

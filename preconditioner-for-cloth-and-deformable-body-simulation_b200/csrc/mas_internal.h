@@ -162,9 +162,19 @@ struct Context
 	// ---- apply-time state
 	DevBuf<float4> coarseR, coarseZ, coarseZsum;  // indexed by node - nVC
 	DevBuf<float4> rIn, zOut;                      // staging for host r / z
-	cudaGraphExec_t applyGraph = nullptr;
-	const float* graphR = nullptr;
-	float* graphZ = nullptr;
+	// instantiated apply graphs, one per (residual, z) pointer pair the caller uses (a solver may precondition more than one
+	// vector pair per iteration); least recently used slot is recycled
+	struct ApplyGraphSlot
+	{
+		cudaGraphExec_t exec = nullptr;
+		const float* r = nullptr;
+		float* z = nullptr;
+		unsigned long long lastUse = 0;
+	};
+	static constexpr int kApplyGraphSlots = 4;
+	ApplyGraphSlot applyGraphs[kApplyGraphSlots];
+	unsigned long long applyGraphClock = 0;
+	const float* phaseR = nullptr;   // residual of the running mas_apply_begin / _end pair
 	int applyLaunches = 0;
 	int prepareLaunches = 0;
 

@@ -312,7 +312,7 @@ def test_stencil_counts_grow_and_shrink_between_prepares(gpu_cls, synth):
 @pytest.mark.parametrize("n", [64, 512])
 def test_three_thousand_graph_replays_are_bit_identical(n, gpu_cls, synth):
     """Soak: 3,000 back-to-back applies of the captured graph (coarse chain, head, tail and coarse addition overlap inside it),
-    alternating between two residuals and two output buffers: every z equals the first z of its residual bit for bit, and
+    alternating between two residuals and rotating through seven output buffers: every z equals the first z of its residual bit for bit, and
     nothing of one apply leaks into the next."""
     import torch
     mesh = synth.cloth_rect_device(n, n, torch.device("cuda:0"))
@@ -329,10 +329,14 @@ def test_three_thousand_graph_replays_are_bit_identical(n, gpu_cls, synth):
     first_a, first_b = za.clone(), zb.clone()
     assert not torch.equal(first_a, first_b)
     bad = torch.zeros((), dtype=torch.int64, device="cuda")
+    # six output buffers for the first residual, one for the second: seven (residual, z) pointer pairs in rotation, more than the
+    # context keeps instantiated graphs for (four; the least recently used one is re-captured)
+    zs = [za] + [torch.empty_like(ra) for _ in range(5)]
     for k in range(1500):
-        za.fill_(float("nan"))
-        g.Preconditioning(za, ra)
-        bad += (za != first_a).any().long()
+        z = zs[k % len(zs)]
+        z.fill_(float("nan"))
+        g.Preconditioning(z, ra)
+        bad += (z != first_a).any().long()
         zb.fill_(float("nan"))
         g.Preconditioning(zb, rb)
         bad += (zb != first_b).any().long()
@@ -377,3 +381,22 @@ def test_two_contexts_on_one_gpu_from_two_host_threads(gpu_cls, synth, pkg):
         assert np.abs(together[i][0] - alone[i][0]).max() <= 1e-6 * np.abs(alone[i][0]).max()
         assert abs(together[i][1] - alone[i][1]) <= 1
         assert np.linalg.norm(together[i][2] - alone[i][2]) <= 1e-3 * np.linalg.norm(alone[i][2])
+
+
+def test_phase_split_and_graph_applies_do_not_share_state(gpu_cls, synth):
+    """mas_apply (captured graph, cached per pointer pair) and the phase-split pair mas_apply_begin / mas_apply_end on one
+    object, with pointers chosen so that a shared "last residual" field would replay a stale graph."""
+    import torch
+    mesh = synth.cloth(96)
+    g = gpu_cls(0).setup_from_mesh(mesh)
+    r1 = torch.from_numpy(synth.residual(mesh.nv)).cuda()
+    r2 = (r1 * -2.0).contiguous()
+    z1, z2, z3 = torch.empty_like(r1), torch.empty_like(r1), torch.empty_like(r1)
+    g.Preconditioning(z1, r1)            # graph for (r1, z1)
+    g.apply_begin(r2)
+    g.apply_end(z2)                      # phase split with r2: z2 = M^-1 r2
+    g.Preconditioning(z1, r2)            # new pair (r2, z1): must not replay the (r1, z1) graph
+    g.Preconditioning(z3, r1)
+    torch.cuda.synchronize()
+    assert torch.equal(z1, z2)
+    assert torch.allclose(z3 * -2.0, z2, rtol=0, atol=1e-5 * float(z2.abs().max()))
