@@ -179,7 +179,7 @@ int mas_set_stream(mas_handle_t h, void* cuda_stream);
 int mas_set_option(mas_handle_t h, int key, int value);
 
 /* Shard the 32-node fine domains across `world` GPUs in Morton-contiguous ranges
- * (SURVEY §8e).  Must precede mas_allocate.  Default: rank 0 of 1. */
+ * (SURVEY §8e).  Must precede mas_allocate.  Default: rank 0 of 1.  At most 16 ranks (MAS_ERR_UNSUPPORTED beyond). */
 int mas_set_partition(mas_handle_t h, int rank, int world);
 
 /* replaces m_positions/m_edges/m_faces/m_neighbours + AllocatePrecoditioner (h:44-56, cpp:38-65).

@@ -320,6 +320,7 @@ int mas_set_partition(mas_handle_t h, int rank, int world)
 {
 	if (!h || world < 1 || rank < 0 || rank >= world) return MAS_ERR_INVALID;
 	if (h->allocated) return fail(h, MAS_ERR_INVALID, "mas_set_partition must precede mas_allocate");
+	if (world > 16) return fail(h, MAS_ERR_UNSUPPORTED, "at most 16 ranks (the GPUs of one box)");
 	h->rank = rank;
 	h->world = world;
 	return MAS_OK;

@@ -354,6 +354,8 @@ def test_errors_are_reported_not_swallowed(gpu_cls, synth, pkg):
     rd = torch.from_numpy(r).cuda()
     with pytest.raises(pkg.MasError, match="overlap"):
         g.Preconditioning(rd, rd)
+    with pytest.raises(pkg.MasError, match="at most 16 ranks"):
+        gpu_cls(0, rank=0, world=17)
     with pytest.raises(pkg.MasError):
         g.Preconditioning(np.zeros((mesh.nv, 4), np.float64), synth.residual(mesh.nv))
 
