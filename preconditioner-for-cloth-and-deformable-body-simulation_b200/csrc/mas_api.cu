@@ -191,7 +191,7 @@ static void free_all(Context* c)
 	release(c->scanTotal); release(c->coarseTables);
 	release(c->diagIn); release(c->offdiagIn); release(c->rangesIn); release(c->efIn); release(c->eeIn); release(c->vfIn);
 	release(c->extraFine); release(c->cooCount); release(c->cooStart); release(c->cooFill); release(c->cooVal);
-	release(c->coarseAcc); release(c->packedInv); release(c->posTab); release(c->posTab96); release(c->invertErr);
+	release(c->coarseAcc); release(c->packedInv); release(c->posTab); release(c->posTab96); release(c->invertErr); release(c->inputErr);
 	release(c->coarseR); release(c->coarseZ); release(c->coarseZsum); release(c->rIn); release(c->zOut);
 	release(c->pcgR); release(c->pcgB); release(c->pcgX);
 	release(c->pcgPartials); release(c->pcgState); release(c->pcgDiag); release(c->pcgOff); release(c->pcgRanges); release(c->pcgIdx);
@@ -326,6 +326,29 @@ int mas_set_partition(mas_handle_t h, int rank, int world)
 	return MAS_OK;
 }
 
+// Input check of mas_allocate, before anything dereferences the caller's indices: the adjacency rows are ordered
+// (starts[0] = 0, non-decreasing, starts[nv] = nnz) and every neighbour, edge and face vertex lies inside the mesh.  The
+// reference trusts its caller and reads out of bounds otherwise.
+__global__ void validate_mesh_kernel(const int* __restrict__ starts, const int* __restrict__ idx, const int4* __restrict__ edges,
+	const int4* __restrict__ faces, int nv, int nnz, int ne, int nf, int* __restrict__ inputErr)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	int bad = 0;
+	if (i < nv && (starts[i] > starts[i + 1] || (i == 0 && starts[0] != 0) || (i == nv - 1 && starts[nv] != nnz))) bad |= 1;
+	if (i < nnz && (idx[i] < 0 || idx[i] >= nv)) bad |= 2;
+	if (i < ne)
+	{
+		const int4 e = edges[i];
+		if (e.x < 0 || e.x >= nv || e.y < 0 || e.y >= nv) bad |= 4;
+	}
+	if (i < nf)
+	{
+		const int4 f = faces[i];
+		if (f.x < 0 || f.x >= nv || f.y < 0 || f.y >= nv || f.z < 0 || f.z >= nv) bad |= 8;
+	}
+	if (bad) atomicOr(inputErr, bad);
+}
+
 int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const float* positions, const int* edges,
 	const int* faces, const int* nbrStarts, const int* nbrIdx, int mem)
 {
@@ -372,6 +395,22 @@ int mas_allocate(mas_handle_t h, int numVerts, int numEdges, int numFaces, const
 	if (numEdges > 0 && edges) MAS_CUDA(c, cudaMemcpyAsync(c->edges.p, edges, sizeof(int4) * (size_t)numEdges, kind, c->stream));
 	if (numFaces > 0 && faces) MAS_CUDA(c, cudaMemcpyAsync(c->faces.p, faces, sizeof(int4) * (size_t)numFaces, kind, c->stream));
 	(void)dEdges; (void)dFaces;
+	{
+		if (int rc = reserve(c, c->inputErr, 1)) return rc;
+		MAS_CUDA(c, cudaMemsetAsync(c->inputErr.p, 0, sizeof(int), c->stream));
+		long long most = numVerts;
+		for (long long n : { (long long)nnz, (long long)(edges ? numEdges : 0), (long long)(faces ? numFaces : 0) }) most = n > most ? n : most;
+		validate_mesh_kernel<<<(unsigned)cdiv(most, 256), 256, 0, c->stream>>>(dStarts, dIdx, c->edges.p, c->faces.p, numVerts, nnz,
+			edges ? numEdges : 0, faces ? numFaces : 0, c->inputErr.p);
+		int bad = 0;
+		MAS_CUDA(c, cudaMemcpyAsync(&bad, c->inputErr.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		MAS_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (bad)
+			return fail(c, MAS_ERR_INVALID, bad & 1 ? "AllocatePrecoditioner: the adjacency row starts are not ordered from 0 to nnz"
+				: bad & 2 ? "AllocatePrecoditioner: a neighbour index lies outside the mesh"
+				: bad & 4 ? "AllocatePrecoditioner: an edge names a vertex outside the mesh"
+				: "AllocatePrecoditioner: a face names a vertex outside the mesh");
+	}
 
 	// Morton-contiguous shard of fine banks for this rank
 	const int nFine = c->nVC / 32;

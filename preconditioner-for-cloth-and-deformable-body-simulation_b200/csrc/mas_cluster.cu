@@ -37,16 +37,23 @@ __device__ __forceinline__ unsigned lanemask_lt(unsigned lane) { return (1u << l
 __device__ __forceinline__ float ldf(const unsigned char* p, int off) { return *reinterpret_cast<const float*>(p + off); }
 __device__ __forceinline__ int ldi(const unsigned char* p, int off) { return *reinterpret_cast<const int*>(p + off); }
 
-// valid flag per candidate stencil (cpp:330, 359, 385)
+// valid flag per candidate stencil (cpp:330, 359, 385).  An id beyond the mesh (the reference would read past its edge / face
+// arrays) drops the stencil and raises *inputErr, which fails the prepare.
 __global__ void stencil_flag_kernel(const unsigned char* __restrict__ ef, const unsigned char* __restrict__ ee,
-	const unsigned char* __restrict__ vf, int efN, int eeN, int total, int fix, int* __restrict__ flag)
+	const unsigned char* __restrict__ vf, int efN, int eeN, int total, int fix, int nv, int ne, int nf, int* __restrict__ flag,
+	int* __restrict__ inputErr)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= total) return;
 	// Q2: the reference reads every kind at the GLOBAL stencil index; MAS_OPT_STENCIL_FIX reads each array from its own zero
 	const int local = i < efN ? i : (fix ? (i < efN + eeN ? i - efN : i - efN - eeN) : i);
 	const unsigned char* rec = (i < efN ? ef : (i < efN + eeN ? ee : vf)) + 48 * (size_t)local;
-	flag[i] = (ldi(rec, 0) >= 0 && ldi(rec, 4) >= 0) ? 1 : 0;
+	const int id0 = ldi(rec, 0), id1 = ldi(rec, 4);
+	// EfSet: edge, face;  EeSet: edge, edge;  VfSet: vertex, face
+	const int lim0 = i < efN + eeN ? ne : nv, lim1 = i < efN ? nf : (i < efN + eeN ? ne : nf);
+	const bool valid = id0 >= 0 && id1 >= 0, inside = id0 < lim0 && id1 < lim1;
+	if (valid && !inside) atomicOr(inputErr, 1);
+	flag[i] = (valid && inside) ? 1 : 0;
 }
 
 __global__ void stencil_build_kernel(const unsigned char* __restrict__ ef, const unsigned char* __restrict__ ee,
@@ -372,13 +379,21 @@ int build_stencils(Context* c, const void* ef, const void* ee, const void* vf, u
 	if (int rc = reserve(c, c->stencilFlag, (size_t)n)) return rc;
 	if (int rc = reserve(c, c->stencilSlot, (size_t)n)) return rc;
 	if (int rc = reserve(c, c->scanTotal, 1)) return rc;
+	if (int rc = reserve(c, c->inputErr, 1)) return rc;
+	MAS_CUDA(c, cudaMemsetAsync(c->inputErr.p, 0, sizeof(int), s));
 	stencil_flag_kernel<<<cdiv(n, threads), threads, 0, s>>>((const unsigned char*)ef, (const unsigned char*)ee,
-		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->optStencilFix, c->stencilFlag.p);
+		(const unsigned char*)vf, (int)efN, (int)eeN, n, c->optStencilFix, c->nv, c->ne, c->nf, c->stencilFlag.p, c->inputErr.p);
 	if (int rc = launch_exclusive_scan(c, c->stencilFlag.p, n, c->stencilSlot.p, c->scanTotal.p)) return rc;
 	c->prepareLaunches += 2;
-	int count = 0;
+	int count = 0, bad = 0;
 	MAS_CUDA(c, cudaMemcpyAsync(&count, c->scanTotal.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+	MAS_CUDA(c, cudaMemcpyAsync(&bad, c->inputErr.p, sizeof(int), cudaMemcpyDeviceToHost, s));
 	MAS_CUDA(c, cudaStreamSynchronize(s));
+	if (bad)
+	{
+		c->err = "PreparePreconditioner: a collision stencil names an edge, face or vertex beyond the mesh";
+		return MAS_ERR_INVALID;
+	}
 	c->nStencil = count;
 	if (count == 0) return MAS_OK;
 	if (int rc = reserve(c, c->stencils, (size_t)count)) return rc;

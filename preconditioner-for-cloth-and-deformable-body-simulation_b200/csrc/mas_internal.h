@@ -157,6 +157,7 @@ struct Context
 	DevBuf<float> packedInv;             // [nBlocks][kTri]
 	DevBuf<unsigned short> posTab;       // packed positions of the CUDA-core inversion kernel's register-tile outputs
 	DevBuf<unsigned short> posTab96;     // tensor-core inversion kernel: packed position of (r, c), r >= c
+	DevBuf<int> inputErr;                // raised by the input checks (adjacency / edge / face / stencil ids beyond the mesh)
 	DevBuf<int> invertErr;               // set by the tensor-core kernel if an MMA completion wait timed out
 
 	// ---- apply-time state

@@ -155,6 +155,7 @@ inline unsigned __reduce_or_sync(unsigned mask, unsigned v)      // every lane p
 	return r;
 }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v)
 {
 	unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);

@@ -35,11 +35,11 @@ int main()
 	const long long cap = (long long)nv * kMaxCollisionPerVert;
 	if (total > cap) total = cap;
 	const int n = (int)total, threads = 256;
-	int count = 0;
+	int count = 0, inputErr = 0;
 	std::vector<int> flag((size_t)n + 1), slot((size_t)n + 1);
 	if (n > 0)
 	{
-		emu::launch(cdiv(n, threads), threads, [&] { stencil_flag_kernel(ef.data(), ee.data(), vf.data(), efN, eeN, n, fix, flag.data()); });
+		emu::launch(cdiv(n, threads), threads, [&] { stencil_flag_kernel(ef.data(), ee.data(), vf.data(), efN, eeN, n, fix, nv, ne, nf, flag.data(), &inputErr); });
 		emu::launch(1, kScanThreads, [&] { exclusive_scan_kernel(flag.data(), n, slot.data(), &count); });
 	}
 	std::vector<Stencil> out((size_t)(count > 0 ? count : 1));

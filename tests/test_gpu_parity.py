@@ -356,6 +356,30 @@ def test_errors_are_reported_not_swallowed(gpu_cls, synth, pkg):
         g.Preconditioning(rd, rd)
     with pytest.raises(pkg.MasError, match="at most 16 ranks"):
         gpu_cls(0, rank=0, world=17)
+    # indices beyond the mesh are caught before any kernel follows them (the reference reads out of bounds)
+    bad = synth.cloth(8)
+    bad.nbr_idx = bad.nbr_idx.copy()
+    bad.nbr_idx[5] = bad.nv
+    with pytest.raises(pkg.MasError, match="neighbour index"):
+        gpu_cls(0).setup_from_mesh(bad)
+    bad = synth.cloth(8)
+    bad.nbr_starts = bad.nbr_starts.copy()
+    bad.nbr_starts[3] = bad.nbr_starts[4] + 1                          # row 3 would end before it starts
+    with pytest.raises(pkg.MasError, match="row starts"):
+        gpu_cls(0).setup_from_mesh(bad)
+    m = synth.cloth(24, with_topology=True)
+    coll = synth.add_collisions(m, 20, 20, 40)
+    ok_ef = coll.ef.copy()
+    gc = gpu_cls(0)
+    coll.ef = coll.ef.copy()
+    coll.ef["fId"][3] = coll.nf + 7                                     # EfSet 3: face id beyond the mesh
+    with pytest.raises(pkg.MasError, match="beyond the mesh"):
+        gc.setup_from_mesh(coll)
+    coll.ef = ok_ef                                                     # the object is still good for a correct prepare
+    gc.PreparePreconditioner(coll.diag, coll.offdiag, coll.nbr_starts, coll.ef, coll.ee, coll.vf, coll.ef_total, coll.ee_total,
+                             coll.vf_total)
+    zc = gc.Preconditioning(np.zeros_like(synth.residual(coll.nv)), synth.residual(coll.nv))
+    assert np.isfinite(zc).all() and np.abs(zc).max() > 0
     with pytest.raises(pkg.MasError):
         g.Preconditioning(np.zeros((mesh.nv, 4), np.float64), synth.residual(mesh.nv))
 
