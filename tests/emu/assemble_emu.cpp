@@ -88,7 +88,7 @@ int main()
 	fa.nv = nv; fa.nVC = nVC; fa.numLevel = L; fa.bankBegin = 0;
 
 	// assemble_and_invert_begin
-	if (L > 1) emu::launch(cdiv(nVC, 256), 256, [&] { cross_bank_kernel(fa, 0, nVC); });
+	if (L > 1) emu::launch(cdiv(nVC, 256), 256, [&] { if (L >= 5) cross_bank_kernel<true>(fa, 0, nVC); else cross_bank_kernel<false>(fa, 0, nVC); });
 	emu::launch(nFine, kInvThreads, [&] { fine_assemble_invert_kernel(fa); });
 	// assemble_and_invert_end
 	for (int level = 1; level + 1 < L; ++level)
