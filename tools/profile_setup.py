@@ -9,7 +9,7 @@ S = pkg.synth
 n = int(os.environ.get("MAS_N", 1024))
 g = pkg.SeSchwarzPreconditioner(0)
 if os.environ.get("MAS_CONFIG") is not None:          # a BASELINE config (synth.config), inputs resident on the device
-    mesh = S.config(int(os.environ["MAS_CONFIG"]))
+    mesh = S.config(int(os.environ["MAS_CONFIG"]), proximity=bool(os.environ.get("MAS_PROXIMITY")))
     g.setup_from_mesh(mesh, device_inputs=True)
     d = g._dev_inputs
     prepare = lambda: g.PreparePreconditioner(d[0], d[1], d[2], d[3], d[4], d[5], mesh.ef_total, mesh.ee_total, mesh.vf_total)
