@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-MAS_N=1024 timeout 300 python tools/profile_setup.py 2>/dev/null | grep -E "prepare device|cross_bank"
-MAS_CONFIG=3 timeout 300 python tools/profile_setup.py 2>/dev/null | grep -E "prepare device|cross_bank"
-MAS_N=2048 timeout 300 python tools/profile_setup.py 2>/dev/null | grep -E "prepare device|cross_bank"
+MAS_CONFIG=1 MAS_PROXIMITY=1 timeout 600 python tools/profile_setup.py > gpurun_out/r2_setup_timeline_cfg1p.txt 2>gpurun_out/r2_setup_timeline_cfg1p.err; cat gpurun_out/r2_setup_timeline_cfg1p.txt; tail -3 gpurun_out/r2_setup_timeline_cfg1p.err
